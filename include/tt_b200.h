@@ -1,0 +1,106 @@
+/* tt_b200.h - C ABI of the B200-native two-tower hot path (libtt_b200.so).
+ *
+ * The reference (gauravchak/two_tower_models) has no FFI of its own: its hot path is a set of PyTorch
+ * library calls inside nn.Module methods.  Each entry point below replaces one such call site; the
+ * host-side mirror in two_tower_models_b200/ binds them with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - matrices are row-major; `ld*` is the row pitch in ELEMENTS; bf16 operand matrices consumed by
+ *     tensor-core kernels need 16-byte aligned bases and pitches that are multiples of 8 elements;
+ *   - ids are int64 (the reference's dtype), floats are fp32, "bf16" is stored as uint16 bits;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises the host, so every
+ *     entry point is CUDA-graph capturable;
+ *   - inputs are borrowed and never written; outputs and workspaces are caller-owned;
+ *   - return value 0 = success, negative = error, message via tt_last_error() (thread-local).
+ *     There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_B200_ABI_VERSION 1
+
+int tt_abi_version(void);
+const char* tt_last_error(void);
+/* Number of SMs of the current device (148 on B200); negative on error. */
+int tt_device_sm_count(void);
+
+/* ---- data movement (HBM-bound helpers) ------------------------------------------------------ */
+
+/* dst[r, 0:dst_cols] = bf16(src[r, 0:cols]) zero-padded.  Packs fp32 features / weights for the
+ * tensor-core kernels (inputs of nn.Linear, reference src/two_tower_base_retrieval.py:76-80). */
+int tt_cast_rows_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst_bf16, int64_t ld_dst,
+                      int64_t dst_cols, void* stream);
+
+/* nn.Embedding lookup (reference :126, :209): dst[i, 0:dim] = table[ids[i], :].
+ * Out-of-range ids are clamped and *oob_flag (may be NULL) is set to 1. */
+int tt_gather_rows_bf16(const float* table, int64_t table_rows, int64_t dim, const int64_t* ids, int64_t n,
+                        void* dst_bf16, int64_t ld_dst, int32_t* oob_flag, void* stream);
+int tt_gather_rows_f32(const float* table, int64_t table_rows, int64_t dim, const int64_t* ids, int64_t n,
+                       float* dst, int64_t ld_dst, int32_t* oob_flag, void* stream);
+
+/* Dense embedding gradient (autograd of nn.Embedding): grad[ids[i], :] += src[i, :].
+ * Exactly one of src_bf16 / src_f32 is non-NULL. */
+int tt_scatter_add_rows(const void* src_bf16, const float* src_f32, int64_t ld_src, const int64_t* ids, int64_t n,
+                        int64_t dim, float* table_grad, int64_t table_rows, void* stream);
+
+/* Bias gradient: out[c] += sum_r src[r, c]. */
+int tt_colsum(const void* src_bf16, const float* src_f32, int64_t rows, int64_t cols, int64_t ld, float* out,
+              void* stream);
+
+/* ---- tcgen05 GEMM --------------------------------------------------------------------------- */
+
+/* C[M,N] (+)= alpha * A * B^T (+ bias[N]) (ReLU) (zeroed where relu_mask <= 0).
+ * A: bf16 [M,K] pitch lda, or (a_mn_major) stored as [K,M] pitch lda.  B: bf16 [N,K] or (b_mn_major) [K,N].
+ * Outputs: c_f32 (pitch ldc_f32) and/or c_bf16 (pitch ldc_bf16).  accumulate != 0: split-K with fp32
+ * atomicAdd into c_f32 (no bias/relu/mask/bf16 output; caller initialises c_f32); split_k 0 = auto.
+ * Replaces nn.Linear forward/backward (reference :76-80, :90-93, :101-110) and the MHA in/out
+ * projections (src/user_history_encoder.py:60-67). */
+int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
+                 int64_t M, int64_t N, int64_t K, const float* bias, int32_t relu, const void* relu_mask_bf16,
+                 int64_t ld_mask, float alpha, float* c_f32, int64_t ldc_f32, void* c_bf16, int64_t ldc_bf16,
+                 int32_t accumulate, int32_t split_k, void* stream);
+
+/* ---- in-batch sampled-softmax loss ---------------------------------------------------------- */
+
+/* Scratch bytes needed by tt_inbatch_ce_fwd / _bwd for this shape on the current device. */
+int64_t tt_inbatch_ce_workspace_bytes(int64_t B, int64_t N, int64_t d);
+
+/* ce[i] = logsumexp_j(U_i . V_j) - U_i . V_{i+target_offset},  lse[i] = logsumexp_j(U_i . V_j).
+ * U: bf16 [B,d], V: bf16 [N,d].  Replaces torch.matmul + F.cross_entropy(reduction="none") with
+ * target = arange (reference src/two_tower_base_retrieval.py:287, :301, :310-312); target_offset is the
+ * multi-GPU generalisation (local users scored against all-gathered items).  d <= 256. */
+int tt_inbatch_ce_fwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                      int64_t target_offset, float* ce, float* lse, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* Backward for upstream g[i] = dL/dce[i]:  dS = g_i (softmax(S)_ij - [j == i+off]);  dU = dS V;  dV = dS^T U.
+ * Any of dU_f32/dU_bf16/dV_f32/dV_bf16 may be NULL (a NULL pair skips that pass). */
+int tt_inbatch_ce_bwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                      int64_t target_offset, const float* lse, const float* g, float* dU_f32, int64_t lddu,
+                      void* dU_bf16, int64_t lddu16, float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- history encoder helpers ---------------------------------------------------------------- */
+
+/* x_bf16[b*H+h, :] = bf16(table[ids[b,h]] + pe[h]) (pe may be NULL);  mean[b, :] = mean_h table[ids[b,h]].
+ * Reference: src/two_tower_with_user_history_encoder.py:105, src/user_history_encoder.py:89-95. */
+int tt_history_gather_pool(const float* table, int64_t table_rows, int64_t D, const int64_t* ids, int64_t B, int64_t H,
+                           const float* pe, void* x_bf16, int64_t ldx, float* mean, int64_t ldmean, int32_t* oob_flag,
+                           void* stream);
+/* table_grad[ids[b,h], :] += dx_bf16[b*H+h, :] + dmean[b, :] / H   (either source may be NULL). */
+int tt_history_scatter_grad(const void* dx_bf16, int64_t lddx, const float* dmean, int64_t lddmean, const int64_t* ids,
+                            int64_t B, int64_t H, int64_t D, float* table_grad, int64_t table_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */

@@ -1,0 +1,63 @@
+"""ctypes binding of libtt_b200.so (the C ABI declared in include/tt_b200.h).
+
+There is deliberately no fallback: if the library is missing, or a compute entry point is called
+without a CUDA device, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
+
+_lib = None
+
+P = c_void_p
+I64 = c_int64
+I32 = c_int32
+F32 = c_float
+
+# name -> (restype, argtypes); mirrors include/tt_b200.h one to one
+SIGNATURES = {
+    "tt_abi_version": (I32, []),
+    "tt_last_error": (c_char_p, []),
+    "tt_device_sm_count": (I32, []),
+    "tt_cast_rows_bf16": (I32, [P, I64, I64, I64, P, I64, I64, P]),
+    "tt_gather_rows_bf16": (I32, [P, I64, I64, P, I64, P, I64, P, P]),
+    "tt_gather_rows_f32": (I32, [P, I64, I64, P, I64, P, I64, P, P]),
+    "tt_scatter_add_rows": (I32, [P, P, I64, P, I64, I64, P, I64, P]),
+    "tt_colsum": (I32, [P, P, I64, I64, I64, P, P]),
+    "tt_gemm_bf16": (I32, [P, I64, I32, P, I64, I32, I64, I64, I64, P, I32, P, I64, F32, P, I64, P, I64, I32, I32, P]),
+    "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
+    "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
+    "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, I64, P]),
+    "tt_history_gather_pool": (I32, [P, I64, I64, P, I64, I64, P, P, I64, P, I64, P, P]),
+    "tt_history_scatter_grad": (I32, [P, I64, P, I64, P, I64, I64, I64, P, I64, P]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python two_tower_models_b200/csrc/build.py` "
+            "(two_tower_models_b200 has no CPU or PyTorch fallback)"
+        )
+    l = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if l.tt_abi_version() != 1:
+        raise RuntimeError("libtt_b200.so ABI version mismatch")
+    _lib = l
+    return l
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().tt_last_error().decode(errors="replace")
+        raise RuntimeError(f"tt_b200 {what} failed (rc={rc}): {msg}")

@@ -1,0 +1,142 @@
+// C ABI (include/tt_b200.h) over the kernel translation units + shared host utilities.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/tt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 1;
+  cached = n;
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  TT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver / device)");
+  TT_CHECK(((uintptr_t)base % 16) == 0 && (pitch_elems % 8) == 0, "tensor map: base/pitch not 16-byte aligned");
+  TT_CHECK(box_inner * 2 <= 128 && box_outer <= 256, "tensor map: box too large");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu pitch=%llu box=%ux%u)",
+           (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_inner, box_outer);
+  return 0;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
+const char* tt_last_error(void) { return g_err; }
+
+int tt_device_sm_count(void) {
+  int dev = 0, n = 0;
+  TT_CUDA(cudaGetDevice(&dev));
+  TT_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+
+int tt_cast_rows_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst, int64_t ld_dst,
+                      int64_t dst_cols, void* stream) {
+  return cast_rows_bf16(src, rows, cols, ld_src, dst, ld_dst, dst_cols, S(stream));
+}
+int tt_gather_rows_bf16(const float* table, int64_t table_rows, int64_t dim, const int64_t* ids, int64_t n, void* dst,
+                        int64_t ld_dst, int32_t* oob_flag, void* stream) {
+  return gather_rows_bf16(table, table_rows, dim, (const long long*)ids, n, dst, ld_dst, oob_flag, S(stream));
+}
+int tt_gather_rows_f32(const float* table, int64_t table_rows, int64_t dim, const int64_t* ids, int64_t n, float* dst,
+                       int64_t ld_dst, int32_t* oob_flag, void* stream) {
+  return gather_rows_f32(table, table_rows, dim, (const long long*)ids, n, dst, ld_dst, oob_flag, S(stream));
+}
+int tt_scatter_add_rows(const void* src16, const float* src32, int64_t ld_src, const int64_t* ids, int64_t n,
+                        int64_t dim, float* table_grad, int64_t table_rows, void* stream) {
+  return scatter_add_rows(src16, src32, ld_src, (const long long*)ids, n, dim, table_grad, table_rows, S(stream));
+}
+int tt_colsum(const void* src16, const float* src32, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream) {
+  return colsum(src16, src32, rows, cols, ld, out, S(stream));
+}
+
+int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
+                 int64_t M, int64_t N, int64_t K, const float* bias, int32_t relu, const void* relu_mask, int64_t ld_mask,
+                 float alpha, float* c_f32, int64_t ldc_f32, void* c_bf16, int64_t ldc_bf16, int32_t accumulate,
+                 int32_t split_k, void* stream) {
+  GemmDesc d;
+  d.A = A; d.lda = lda; d.a_mn_major = a_mn_major;
+  d.B = B; d.ldb = ldb; d.b_mn_major = b_mn_major;
+  d.M = M; d.N = N; d.K = K;
+  d.bias = bias; d.relu = relu; d.relu_mask = relu_mask; d.ld_mask = ld_mask;
+  d.alpha = alpha;
+  d.c32 = c_f32; d.ldc32 = ldc_f32; d.c16 = c_bf16; d.ldc16 = ldc_bf16;
+  d.accumulate = accumulate; d.split_k = split_k;
+  return gemm_bf16(d, S(stream));
+}
+
+int64_t tt_inbatch_ce_workspace_bytes(int64_t B, int64_t N, int64_t d) {
+  return (int64_t)inbatch_ce_workspace_bytes(B, N, d);
+}
+int tt_inbatch_ce_fwd(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                      int64_t target_offset, float* ce, float* lse, void* ws, int64_t ws_bytes, void* stream) {
+  return inbatch_ce_fwd(U, ldu, V, ldv, B, N, d, target_offset, ce, lse, ws, (size_t)ws_bytes, S(stream));
+}
+int tt_inbatch_ce_bwd(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                      int64_t target_offset, const float* lse, const float* g, float* dU, int64_t lddu, void* dU16,
+                      int64_t lddu16, float* dV, int64_t lddv, void* dV16, int64_t lddv16, void* ws, int64_t ws_bytes,
+                      void* stream) {
+  return inbatch_ce_bwd(U, ldu, V, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16, lddv16,
+                        ws, (size_t)ws_bytes, S(stream));
+}
+
+int tt_history_gather_pool(const float* table, int64_t table_rows, int64_t D, const int64_t* ids, int64_t B, int64_t H,
+                           const float* pe, void* x16, int64_t ldx, float* mean, int64_t ldmean, int32_t* oob_flag,
+                           void* stream) {
+  return history_gather_pool(table, table_rows, D, (const long long*)ids, B, H, pe, x16, ldx, mean, ldmean, oob_flag, S(stream));
+}
+int tt_history_scatter_grad(const void* dx16, int64_t lddx, const float* dmean, int64_t lddmean, const int64_t* ids,
+                            int64_t B, int64_t H, int64_t D, float* table_grad, int64_t table_rows, void* stream) {
+  return history_scatter_grad(dx16, lddx, dmean, lddmean, (const long long*)ids, B, H, D, table_grad, table_rows, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,691 @@
+// Fused in-batch sampled-softmax cross entropy for sm_100a (forward and backward).
+//
+// Reference semantics: src/two_tower_base_retrieval.py:287 (S = U V^T), :301 (target = arange),
+// :310-312 (F.cross_entropy(reduction="none")) and autograd of the same (train/train.py:124).
+// The [B,N] score matrix never exists in HBM: 128xBN score tiles are produced by tcgen05.mma into
+// TMEM from TMA-staged bf16 operand tiles and consumed in place.
+//
+//   forward : per 128-row tile, running (max, sum-exp) over column tiles + the target logit.
+//   backward: one generic "flash" kernel  acc[128, d] = sum_j E_j * Y_j,  E_j = f(X Y_j^T), run twice:
+//       pass A  X=U, Y=V, E_ij = g_i (exp(S_ij - lse_i) - [j == i+off])           -> dU
+//       pass B  X=V, Y=U, E_ji = g_i (exp(S_ij - lse_i) - [j == i+off]) (col stats) -> dV
+//     E is written as bf16 into a 128B-swizzled smem tile and fed back as the A operand of the second
+//     UMMA, whose B operand is the same Y tile read MN-major.
+//
+// Work is the flattened (row tile, column tile) space cut into equal contiguous ranges, one per SM
+// (persistent CTAs).  A CTA's range touches <= a few row tiles ("segments"); every segment writes a
+// partial result into a slot and a small second kernel merges the slots.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
+// warps 4-7 / 8-11 two epilogue warpgroups that alternate score tiles (TMEM buffer e <-> group e).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tt {
+
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+struct SegIter {
+  long long f, f1;
+  int CT;
+  __device__ SegIter(long long T, long long total, int ct) {
+    f = (long long)blockIdx.x * T;
+    f1 = f + T < total ? f + T : total;
+    CT = ct;
+  }
+  __device__ bool next(int& r, int& j0, int& j1) {
+    if (f >= f1) return false;
+    r = (int)(f / CT);
+    j0 = (int)(f % CT);
+    long long rem = f1 - f;
+    j1 = (long long)j0 + rem < CT ? (int)(j0 + rem) : CT;
+    f += j1 - j0;
+    return true;
+  }
+};
+
+struct Sched {
+  long long T, total;
+  int XT, CT, max_slots, grid;
+};
+static Sched make_sched(long long x_rows, long long y_rows, int BN) {
+  Sched s;
+  s.XT = (int)((x_rows + 127) / 128);
+  s.CT = (int)((y_rows + BN - 1) / BN);
+  s.total = (long long)s.XT * s.CT;
+  s.grid = (int)(s.total < num_sms() ? s.total : num_sms());
+  s.T = (s.total + s.grid - 1) / s.grid;
+  s.grid = (int)((s.total + s.T - 1) / s.T);
+  s.max_slots = (int)((s.CT + s.T - 1) / s.T) + 1;
+  return s;
+}
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+struct CeFwdArgs {
+  int B, N;
+  long long target_offset;
+  long long T, total;
+  int CT;
+  long long Bpad;
+  float* part_m;
+  float* part_s;
+  float* diag;
+};
+
+template <int DP>
+struct CeFwdCfg {
+  static constexpr int BN = 128;
+  static constexpr int KBOX = DP / 64;
+  static constexpr int X_BYTES = 128 * DP * 2;
+  static constexpr int Y_BYTES = BN * DP * 2;
+  static constexpr int STAGES = DP == 64 ? 6 : (DP == 128 ? 4 : 2);
+  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + 1024 + 256;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(384, 1)
+ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeFwdArgs a) {
+  using Cfg = CeFwdCfg<DP>;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sx = smem;
+  uint8_t* sy = smem + Cfg::X_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + Cfg::STAGES * Cfg::Y_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + 1;
+  uint64_t* y_full = bars + 2;
+  uint64_t* y_empty = y_full + Cfg::STAGES;
+  uint64_t* s_full = y_empty + Cfg::STAGES;
+  uint64_t* s_empty = s_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmy);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      SegIter it(a.T, a.total, a.CT);
+      int r, j0, j1, stage = 0;
+      uint32_t phase = 0, xs = 0;
+      while (it.next(r, j0, j1)) {
+        mbar_wait(x_empty, (xs & 1) ^ 1);
+        mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
+#pragma unroll
+        for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(sx + b * 16384, &tmx, x_full, b * 64, r * 128);
+        for (int j = j0; j < j1; ++j) {
+          mbar_wait(&y_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&y_full[stage], Cfg::Y_BYTES);
+          uint8_t* dst = sy + stage * Cfg::Y_BYTES;
+#pragma unroll
+          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), &tmy, &y_full[stage], b * 64, j * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ++xs;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      SegIter it(a.T, a.total, a.CT);
+      int r, j0, j1, stage = 0;
+      uint32_t phase = 0, xs = 0, t = 0;
+      const uint32_t sxa = smem_u32(sx);
+      while (it.next(r, j0, j1)) {
+        mbar_wait(x_full, xs & 1);
+        for (int j = j0; j < j1; ++j, ++t) {
+          const uint32_t buf = t & 1, use = t >> 1;
+          mbar_wait(&y_full[stage], phase);
+          mbar_wait(&s_empty[buf], (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t sya = smem_u32(sy + stage * Cfg::Y_BYTES);
+#pragma unroll
+          for (int k = 0; k < DP / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sxa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
+            const uint64_t db = make_smem_desc_sw128(sya + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
+            umma_bf16(tmem_base + buf * BN, da, db, idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&y_empty[stage]);
+          umma_commit(&s_full[buf]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(x_empty);
+        ++xs;
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = (warp - 4) >> 2;  // epilogue group <-> TMEM buffer
+    const int q = warp & 3;
+    SegIter it(a.T, a.total, a.CT);
+    int r, j0, j1;
+    uint32_t t = 0;
+    while (it.next(r, j0, j1)) {
+      const long long row = (long long)r * 128 + q * 32 + lane;
+      const bool valid = row < a.B;
+      const long long tgt = row + a.target_offset;
+      float m = -INFINITY, s = 0.f;
+      for (int j = j0; j < j1; ++j, ++t) {
+        if ((int)(t & 1) != e) continue;
+        const uint32_t use = t >> 1;
+        mbar_wait(&s_full[e], use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const long long n0 = (long long)j * BN + c * 32;
+          if (n0 >= a.N) break;
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * BN + c * 32, v);
+          tmem_wait_ld();
+          if (n0 + 32 > a.N) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i >= a.N) v[i] = -INFINITY;
+          }
+          if (valid && tgt >= n0 && tgt < n0 + 32) {
+            float dg = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i == tgt) dg = v[i];
+            a.diag[row] = dg;
+          }
+          float cm = v[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, v[i]);
+          const float m_new = fmaxf(m, cm * LOG2E);
+          s *= ex2f(m - m_new);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            acc0 += ex2f(fmaf(v[i], LOG2E, -m_new));
+            acc1 += ex2f(fmaf(v[i + 1], LOG2E, -m_new));
+          }
+          s += acc0 + acc1;
+          m = m_new;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[e]);
+      }
+      if (valid) {
+        const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
+        const long long o = (long long)(slot * 2 + e) * a.Bpad + row;
+        a.part_m[o] = m;
+        a.part_s[o] = s;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+__global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, const float* part_m, const float* part_s,
+                                  const float* diag, float* ce, float* lse) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  const long long r = row / 128;
+  const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
+  float M = -INFINITY;
+  for (int sl = 0; sl <= last - first; ++sl)
+    for (int e = 0; e < 2; ++e) M = fmaxf(M, part_m[(long long)(sl * 2 + e) * Bpad + row]);
+  float S = 0.f;
+  for (int sl = 0; sl <= last - first; ++sl)
+    for (int e = 0; e < 2; ++e) {
+      const long long o = (long long)(sl * 2 + e) * Bpad + row;
+      S += part_s[o] * exp2f(part_m[o] - M);
+    }
+  const float l = (M + log2f(S)) * LN2;
+  lse[row] = l;
+  ce[row] = l - diag[row];
+}
+
+static int pick_dp(long long d) { return d <= 64 ? 64 : (d <= 128 ? 128 : 256); }
+
+static size_t fwd_ws_bytes(const Sched& s, long long Bpad) {
+  return (size_t)(2 * (size_t)s.max_slots * 2 * Bpad + Bpad) * sizeof(float);
+}
+static size_t bwd_ws_bytes(const Sched& s, int DP) { return (size_t)s.max_slots * s.XT * 128 * DP * sizeof(float); }
+
+size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d) {
+  const int DP = pick_dp(d);
+  const int BNb = DP == 256 ? 64 : 128;
+  const long long Bpad = (B + 127) / 128 * 128;
+  size_t a = fwd_ws_bytes(make_sched(B, N, 128), Bpad);
+  size_t b = bwd_ws_bytes(make_sched(B, N, BNb), DP);
+  size_t c = bwd_ws_bytes(make_sched(N, B, BNb), DP);
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
+}
+
+template <int DP>
+static int launch_ce_fwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeFwdArgs& a, int grid, cudaStream_t st) {
+  using Cfg = CeFwdCfg<DP>;
+  static bool configured = false;
+  if (!configured) {
+    TT_CUDA(cudaFuncSetAttribute(ce_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  ce_fwd_kernel<DP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
+                   long long target_offset, float* ce, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_fwd: empty problem");
+  TT_CHECK(d <= 256, "inbatch_ce_fwd: embedding dim %lld > 256 is not supported", d);
+  TT_CHECK(target_offset >= 0 && target_offset + B <= N, "inbatch_ce_fwd: targets [%lld, %lld) outside the %lld item columns",
+           target_offset, target_offset + B, N);
+  TT_CHECK((ldu % 8) == 0 && (ldv % 8) == 0 && ((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0,
+           "inbatch_ce_fwd: operands need 16-byte aligned rows");
+  const int DP = pick_dp(d);
+  const Sched s = make_sched(B, N, 128);
+  const long long Bpad = (B + 127) / 128 * 128;
+  TT_CHECK(ws_bytes >= fwd_ws_bytes(s, Bpad), "inbatch_ce_fwd: workspace too small (%zu < %zu)", ws_bytes, fwd_ws_bytes(s, Bpad));
+  CeFwdArgs a;
+  a.B = (int)B; a.N = (int)N; a.target_offset = target_offset;
+  a.T = s.T; a.total = s.total; a.CT = s.CT; a.Bpad = Bpad;
+  a.part_m = (float*)ws;
+  a.part_s = a.part_m + (size_t)s.max_slots * 2 * Bpad;
+  a.diag = a.part_s + (size_t)s.max_slots * 2 * Bpad;
+  CUtensorMap tx, ty;
+  int rc = make_tmap_bf16(&tx, U, d, B, ldu, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&ty, V, d, N, ldv, 64, 128);
+  if (rc) return rc;
+  if (DP == 64) rc = launch_ce_fwd<64>(tx, ty, a, s.grid, stream);
+  else if (DP == 128) rc = launch_ce_fwd<128>(tx, ty, a, s.grid, stream);
+  else rc = launch_ce_fwd<256>(tx, ty, a, s.grid, stream);
+  if (rc) return rc;
+  ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, a.diag, ce, lse);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// Backward (generic two-UMMA kernel)
+// =============================================================================================
+struct CeBwdArgs {
+  int XR, YR;            // valid rows of X / Y
+  long long diag_shift;  // element (row, col) is a positive when col == row + diag_shift
+  long long T, total;
+  int CT;
+  const float* g;    // upstream dL/dce, indexed by user
+  const float* lse;  // indexed by user
+  float* partial;    // [max_slots][XT*128][DP]
+  long long slot_stride;
+};
+
+template <int DP>
+struct CeBwdCfg {
+  static constexpr int BN = DP == 256 ? 64 : 128;
+  static constexpr int KBOX = DP / 64;
+  static constexpr int X_BYTES = 128 * DP * 2;
+  static constexpr int Y_BYTES = BN * DP * 2;
+  static constexpr int P_BYTES = 128 * BN * 2;
+  static constexpr int STAGES = DP == 64 ? 4 : 3;
+  static constexpr int COLSTAT_BYTES = 2 * 2 * BN * 8;  // [group][double buffer][BN] float2
+  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + 2 * P_BYTES + COLSTAT_BYTES + 1024 + 256;
+  static constexpr int ACC_COL = 2 * BN;
+};
+
+template <int DP, bool COLSTATS>
+__global__ void __launch_bounds__(384, 1)
+ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeBwdArgs a) {
+  using Cfg = CeBwdCfg<DP>;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sx = smem;
+  uint8_t* sy = sx + Cfg::X_BYTES;
+  uint8_t* sp = sy + Cfg::STAGES * Cfg::Y_BYTES;
+  float2* scol = reinterpret_cast<float2*>(sp + 2 * Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scol) + Cfg::COLSTAT_BYTES);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + 1;
+  uint64_t* acc_full = bars + 2;
+  uint64_t* acc_empty = bars + 3;
+  uint64_t* s_full = bars + 4;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 8;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* y_full = bars + 12;
+  uint64_t* y_empty = y_full + Cfg::STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmy);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      SegIter it(a.T, a.total, a.CT);
+      int r, j0, j1, stage = 0;
+      uint32_t phase = 0, xs = 0;
+      while (it.next(r, j0, j1)) {
+        mbar_wait(x_empty, (xs & 1) ^ 1);
+        mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
+#pragma unroll
+        for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(sx + b * 16384, &tmx, x_full, b * 64, r * 128);
+        for (int j = j0; j < j1; ++j) {
+          mbar_wait(&y_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&y_full[stage], Cfg::Y_BYTES);
+          uint8_t* dst = sy + stage * Cfg::Y_BYTES;
+#pragma unroll
+          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), &tmy, &y_full[stage], b * 64, j * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ++xs;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);  // S = X Y^T
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, DP, 0, 1);  // acc += E Y   (Y read MN-major)
+      SegIter it(a.T, a.total, a.CT);
+      int r, j0, j1;
+      int stage1 = 0, stage2 = 0;  // Y ring positions of the next UMMA-1 / UMMA-2
+      uint32_t phase1 = 0;
+      uint32_t t1 = 0, t2 = 0, xs = 0;
+      const uint32_t sxa = smem_u32(sx), spa = smem_u32(sp);
+      auto mma1 = [&]() {
+        const uint32_t buf = t1 & 1, use = t1 >> 1;
+        mbar_wait(&y_full[stage1], phase1);
+        mbar_wait(&s_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sya = smem_u32(sy + stage1 * Cfg::Y_BYTES);
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(sxa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
+          const uint64_t db = make_smem_desc_sw128(sya + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
+          umma_bf16(tmem_base + buf * BN, da, db, idesc1, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[buf]);
+        if (++stage1 == Cfg::STAGES) { stage1 = 0; phase1 ^= 1; }
+        ++t1;
+      };
+      auto mma2 = [&](bool first) {
+        const uint32_t buf = t2 & 1, use = t2 >> 1;
+        mbar_wait(&p_full[buf], use & 1);
+        tc_fence_after();
+        const uint32_t sya = smem_u32(sy + stage2 * Cfg::Y_BYTES);
+        const uint32_t pa = spa + buf * Cfg::P_BYTES;
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
+          const uint64_t db = make_smem_desc_sw128(sya + k * 2048, BN * 128, 1024);
+          umma_bf16(tmem_base + Cfg::ACC_COL, da, db, idesc2, (!first || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&y_empty[stage2]);
+        umma_commit(&p_empty[buf]);
+        if (++stage2 == Cfg::STAGES) stage2 = 0;
+        ++t2;
+      };
+      while (it.next(r, j0, j1)) {
+        mbar_wait(x_full, xs & 1);
+        mbar_wait(acc_empty, (xs & 1) ^ 1);
+        mma1();
+        for (int j = j0; j < j1; ++j) {
+          if (j + 1 < j1) mma1();
+          else umma_commit(x_empty);  // all S = X Y^T of this segment issued
+          mma2(j == j0);
+        }
+        umma_commit(acc_full);
+        ++xs;
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int wg_tid = threadIdx.x - 128 - e * 128;  // 0..127 inside the epilogue group
+    SegIter it(a.T, a.total, a.CT);
+    int r, j0, j1;
+    uint32_t t = 0, xs = 0, my_use = 0;
+    uint8_t* my_p = sp + e * Cfg::P_BYTES;
+    const uint32_t prow = q * 32 + lane;  // row of the 128-row tile owned by this thread
+    while (it.next(r, j0, j1)) {
+      const long long row = (long long)r * 128 + prow;
+      const bool valid = row < a.XR;
+      float rs = 1.f, rl = 0.f;
+      if (!COLSTATS) {
+        rs = valid ? a.g[row] : 0.f;
+        rl = valid ? a.lse[row] * LOG2E : 0.f;
+      }
+      const long long tgt = row + a.diag_shift;
+      for (int j = j0; j < j1; ++j, ++t) {
+        if ((int)(t & 1) != e) continue;
+        const uint32_t use = my_use++;
+        float2* cst = scol + (e * 2 + (use & 1)) * BN;
+        if (COLSTATS) {
+          if (wg_tid < BN) {
+            const long long col = (long long)j * BN + wg_tid;
+            const bool cv = col < a.YR;
+            cst[wg_tid] = make_float2(cv ? a.g[col] : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+        }
+        mbar_wait(&s_full[e], use & 1);
+        mbar_wait(&p_empty[e], (use & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const long long n0 = (long long)j * BN + c * 32;
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * BN + c * 32, v);
+          tmem_wait_ld();
+          if (!COLSTATS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
+            if (tgt >= n0 && tgt < n0 + 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i == tgt) v[i] -= rs;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float2 cc = cst[c * 32 + i];
+              v[i] = cc.x * ex2f(fmaf(v[i], LOG2E, -cc.y));
+            }
+            if (tgt >= n0 && tgt < n0 + 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i == tgt) v[i] -= cst[c * 32 + i].x;
+            }
+          }
+          // bf16 pack + swizzled store: columns [c*32, c*32+32) of the P tile = 4 x 16-byte chunks
+          uint8_t* box = my_p + ((c * 32) >> 6) * 16384;
+          const uint32_t chunk0 = ((c * 32) & 63) >> 3;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
+            o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+            o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
+            o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+            *reinterpret_cast<uint4*>(box + sw128_offset(prow, chunk0 + h)) = o;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[e]);
+          mbar_arrive(&p_full[e]);
+        }
+      }
+      // segment accumulator -> partial slot (each group drains half of the columns)
+      mbar_wait(acc_full, xs & 1);
+      tc_fence_after();
+      {
+        const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
+        float* dst = a.partial + (long long)slot * a.slot_stride + row * DP;
+#pragma unroll 1
+        for (int c = 0; c < DP / 64; ++c) {
+          const int col = e * (DP / 2) + c * 32;
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::ACC_COL + col, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(dst + col + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      ++xs;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// out[row, c] = sum over the slots that touched row's tile
+__global__ void ce_bwd_reduce_kernel(int rows, int d, int DP, long long T, int CT, const float* partial,
+                                     long long slot_stride, float* out32, long long ld32, bf16* out16, long long ld16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cpr = DP / 4;
+  const long long row = idx / cpr;
+  const int c = (int)(idx % cpr) * 4;
+  if (row >= rows) return;
+  const long long r = row / 128;
+  const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sl = 0; sl <= last - first; ++sl) {
+    const float4 p = *reinterpret_cast<const float4*>(partial + (long long)sl * slot_stride + row * DP + c);
+    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  }
+  const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+  for (int i = 0; i < 4; ++i) {
+    if (c + i < d) {
+      if (out32) out32[row * ld32 + c + i] = vals[i];
+      if (out16) out16[row * ld16 + c + i] = __float2bfloat16(vals[i]);
+    }
+  }
+}
+
+template <int DP, bool COLSTATS>
+static int launch_ce_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid, cudaStream_t st) {
+  using Cfg = CeBwdCfg<DP>;
+  static bool configured = false;
+  if (!configured) {
+    TT_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<DP, COLSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  ce_bwd_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DP>
+static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr, const void* Y, long long ldy,
+                       long long yr, long long d, long long diag_shift, const float* g, const float* lse, float* out32,
+                       long long ld32, void* out16, long long ld16, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  using Cfg = CeBwdCfg<DP>;
+  const Sched s = make_sched(xr, yr, Cfg::BN);
+  TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
+  CeBwdArgs a;
+  a.XR = (int)xr; a.YR = (int)yr; a.diag_shift = diag_shift;
+  a.T = s.T; a.total = s.total; a.CT = s.CT;
+  a.g = g; a.lse = lse;
+  a.partial = (float*)ws;
+  a.slot_stride = (long long)s.XT * 128 * DP;
+  CUtensorMap tx, ty;
+  int rc = make_tmap_bf16(&tx, X, d, xr, ldx, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&ty, Y, d, yr, ldy, 64, Cfg::BN);
+  if (rc) return rc;
+  rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
+  if (rc) return rc;
+  const long long n = xr * (DP / 4);
+  ce_bwd_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)xr, (int)d, DP, s.T, s.CT, a.partial,
+                                                                         a.slot_stride, out32, ld32, (bf16*)out16, ld16);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
+                   long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
+                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, void* ws, size_t ws_bytes,
+                   cudaStream_t stream) {
+  TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_bwd: empty problem");
+  TT_CHECK(d <= 256, "inbatch_ce_bwd: embedding dim %lld > 256 is not supported", d);
+  TT_CHECK((ldu % 8) == 0 && (ldv % 8) == 0 && ((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0,
+           "inbatch_ce_bwd: operands need 16-byte aligned rows");
+  const int DP = pick_dp(d);
+  int rc = 0;
+#define TT_PASS(DPV)                                                                                                 \
+  do {                                                                                                               \
+    if (dU || dU16)                                                                                                  \
+      rc = ce_bwd_pass<DPV>(false, U, ldu, B, V, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, lddu16, ws,       \
+                            ws_bytes, stream);                                                                       \
+    if (rc == 0 && (dV || dV16))                                                                                     \
+      rc = ce_bwd_pass<DPV>(true, V, ldv, N, U, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, lddv16, ws,       \
+                            ws_bytes, stream);                                                                       \
+  } while (0)
+  if (DP == 64) TT_PASS(64);
+  else if (DP == 128) TT_PASS(128);
+  else TT_PASS(256);
+#undef TT_PASS
+  return rc;
+}
+
+}  // namespace tt

@@ -1,0 +1,205 @@
+// HBM-bound helper kernels: fp32->bf16 row packing, embedding gathers, embedding-gradient scatter-add,
+// column sums (bias gradients) and the history gather + positional-encoding + mean-pool.
+// All accesses are coalesced along the feature dimension; ids are int64 like the reference's.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tt {
+
+// ---------------------------------------------------------------------------------------------
+// fp32 [rows, cols] -> bf16 [rows, dst_cols] (zero padded on the right)
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_rows_kernel(const float* __restrict__ src, long long rows, int cols, long long ld_src,
+                                 bf16* __restrict__ dst, long long ld_dst, int dst_cols) {
+  const int cpr = (dst_cols + 1) / 2;  // column pairs per row
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = idx / cpr;
+  const int c = (int)(idx % cpr) * 2;
+  if (row >= rows) return;
+  const float* s = src + row * ld_src;
+  const float a = c < cols ? s[c] : 0.f;
+  const float b = c + 1 < cols ? s[c + 1] : 0.f;
+  bf16* d = dst + row * ld_dst + c;
+  if (c + 1 < dst_cols && ((ld_dst & 1) == 0)) {
+    *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(a, b);
+  } else {
+    d[0] = __float2bfloat16(a);
+    if (c + 1 < dst_cols) d[1] = __float2bfloat16(b);
+  }
+}
+
+int cast_rows_bf16(const float* src, long long rows, long long cols, long long ld_src, void* dst, long long ld_dst,
+                   long long dst_cols, cudaStream_t stream) {
+  TT_CHECK(rows >= 0 && cols >= 0 && dst_cols >= cols && ld_dst >= dst_cols, "cast_rows_bf16: bad shape");
+  if (rows == 0 || dst_cols == 0) return 0;
+  TT_CHECK(((uintptr_t)dst % 4) == 0, "cast_rows_bf16: dst must be 4-byte aligned");
+  const long long n = rows * ((dst_cols + 1) / 2);
+  cast_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, rows, (int)cols, ld_src, (bf16*)dst, ld_dst, (int)dst_cols);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// embedding gather: one warp per output row
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void gather_rows_kernel(const float* __restrict__ table, long long table_rows, int dim,
+                                   const long long* __restrict__ ids, long long n, OutT* __restrict__ dst,
+                                   long long ld_dst, int* oob_flag) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  long long id = ids[row];
+  if (id < 0 || id >= table_rows) {
+    if (lane == 0 && oob_flag) atomicExch(oob_flag, 1);
+    id = id < 0 ? 0 : table_rows - 1;
+  }
+  const float* s = table + id * dim;
+  OutT* d = dst + row * ld_dst;
+  for (int c = lane; c < dim; c += 32) {
+    if constexpr (sizeof(OutT) == 2) d[c] = __float2bfloat16(s[c]);
+    else d[c] = s[c];
+  }
+}
+
+int gather_rows_bf16(const float* table, long long table_rows, long long dim, const long long* ids, long long n,
+                     void* dst, long long ld_dst, int* oob_flag, cudaStream_t stream) {
+  if (n == 0) return 0;
+  TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_bf16: bad shape");
+  gather_rows_kernel<bf16><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, (bf16*)dst, ld_dst, oob_flag);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+int gather_rows_f32(const float* table, long long table_rows, long long dim, const long long* ids, long long n,
+                    float* dst, long long ld_dst, int* oob_flag, cudaStream_t stream) {
+  if (n == 0) return 0;
+  TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_f32: bad shape");
+  gather_rows_kernel<float><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, dst, ld_dst, oob_flag);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense embedding gradient: table_grad[ids[i], :] += src[i, :]   (duplicates accumulate, like
+// embedding_dense_backward in the reference's autograd)
+// ---------------------------------------------------------------------------------------------
+__global__ void scatter_add_rows_kernel(const bf16* __restrict__ s16, const float* __restrict__ s32, long long ld_src,
+                                        const long long* __restrict__ ids, long long n, int dim,
+                                        float* __restrict__ grad, long long table_rows) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const long long id = ids[row];
+  if (id < 0 || id >= table_rows) return;
+  float* g = grad + id * dim;
+  for (int c = lane; c < dim; c += 32) {
+    const float v = s16 ? __bfloat162float(s16[row * ld_src + c]) : s32[row * ld_src + c];
+    atomicAdd(g + c, v);
+  }
+}
+int scatter_add_rows(const void* src16, const float* src32, long long ld_src, const long long* ids, long long n,
+                     long long dim, float* table_grad, long long table_rows, cudaStream_t stream) {
+  if (n == 0) return 0;
+  TT_CHECK((src16 != nullptr) != (src32 != nullptr), "scatter_add_rows: exactly one source");
+  scatter_add_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[c] += sum_r src[r, c];  out must be initialised by the caller
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const bf16* __restrict__ s16, const float* __restrict__ s32, long long rows, int cols,
+                              long long ld, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = r0 + ry; r < r1; r += 8) acc += s16 ? __bfloat162float(s16[r * ld + c]) : s32[r * ld + c];
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    atomicAdd(out + c, t);
+  }
+}
+int colsum(const void* src16, const float* src32, long long rows, long long cols, long long ld, float* out,
+           cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  TT_CHECK((src16 != nullptr) != (src32 != nullptr), "colsum: exactly one source");
+  const int rpb = 256;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)src16, src32, rows, (int)cols, ld, out, rpb);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// history: x16[b*H + h, :] = bf16(table[ids[b,h]] + pe[h]);  mean[b, :] = mean_h table[ids[b,h]]
+// (mean pooling BEFORE the positional encoding: reference src/user_history_encoder.py:89 vs :95;
+//  history ids index the ITEM table: src/two_tower_with_user_history_encoder.py:105)
+// ---------------------------------------------------------------------------------------------
+__global__ void history_gather_pool_kernel(const float* __restrict__ table, long long table_rows, int D,
+                                           const long long* __restrict__ ids, int H, const float* __restrict__ pe,
+                                           bf16* __restrict__ x16, long long ldx, float* __restrict__ mean,
+                                           long long ldmean, int* oob_flag) {
+  const long long b = blockIdx.x;
+  const float inv = 1.f / (float)H;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sum = 0.f;
+    for (int h = 0; h < H; ++h) {
+      long long id = ids[b * H + h];
+      if (id < 0 || id >= table_rows) {
+        if (oob_flag) atomicExch(oob_flag, 1);
+        id = id < 0 ? 0 : table_rows - 1;
+      }
+      const float v = table[id * D + c];
+      sum += v;
+      x16[(b * H + h) * ldx + c] = __float2bfloat16(v + (pe ? pe[h * D + c] : 0.f));
+    }
+    mean[b * ldmean + c] = sum * inv;
+  }
+}
+int history_gather_pool(const float* table, long long table_rows, long long D, const long long* ids, long long B,
+                        long long H, const float* pe, void* x16, long long ldx, float* mean, long long ldmean,
+                        int* oob_flag, cudaStream_t stream) {
+  if (B == 0) return 0;
+  TT_CHECK(H > 0 && D > 0 && ldx >= D && ldmean >= D, "history_gather_pool: bad shape");
+  const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  history_gather_pool_kernel<<<(unsigned)B, threads, 0, stream>>>(table, table_rows, (int)D, ids, (int)H, pe, (bf16*)x16, ldx, mean, ldmean, oob_flag);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// table_grad[ids[b,h], :] += dx[b*H+h, :] + dmean[b, :] / H
+__global__ void history_scatter_grad_kernel(const bf16* __restrict__ dx16, long long lddx, const float* __restrict__ dmean,
+                                            long long lddmean, const long long* __restrict__ ids, int H, int D,
+                                            float* __restrict__ grad, long long table_rows) {
+  const long long b = blockIdx.x;
+  const float inv = 1.f / (float)H;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float dm = dmean ? dmean[b * lddmean + c] * inv : 0.f;
+    for (int h = 0; h < H; ++h) {
+      const long long id = ids[b * H + h];
+      if (id < 0 || id >= table_rows) continue;
+      const float v = (dx16 ? __bfloat162float(dx16[(b * H + h) * lddx + c]) : 0.f) + dm;
+      atomicAdd(grad + id * D + c, v);
+    }
+  }
+}
+int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, long long lddmean,
+                         const long long* ids, long long B, long long H, long long D, float* table_grad,
+                         long long table_rows, cudaStream_t stream) {
+  if (B == 0) return 0;
+  const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  history_scatter_grad_kernel<<<(unsigned)B, threads, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, (int)H, (int)D, table_grad, table_rows);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tt

@@ -1,0 +1,329 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (+)= alpha * A * B^T  (+bias, ReLU, mask)
+//
+// A is [M,K] (K-major) or, when a_mn, stored as [K,M] (M contiguous: "MN-major", used for X^T * dY weight
+// gradients without materialising a transpose); likewise B is [N,K] or stored [K,N].  bf16 in, fp32
+// accumulate in TMEM, fp32 and/or bf16 out.  One CTA per SM:
+//   warp 0  TMA producer (one lane)     warp 1  UMMA issuer (one lane)     warp 2  TMEM allocator
+//   warps 4-7  epilogue (TMEM -> registers -> global), overlapped with the next tile's main loop through
+//   two TMEM accumulator stages.
+// Used by the tower MLPs (reference src/two_tower_base_retrieval.py:76-80,90-93,101-110), their
+// backward (autograd of the same) and the history encoder's in/out projections
+// (src/user_history_encoder.py:60-67).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tt {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // one 128-byte swizzle atom of bf16 along K
+
+struct GemmArgs {
+  int M, N, K;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  const float* bias;
+  int relu;
+  const bf16* mask;
+  long long ld_mask;
+  float* c32;
+  long long ldc32;
+  int atomic32;
+  bf16* c16;
+  long long ldc16;
+  float alpha;
+  int vec32, vec16, vecmask;
+  int mn_lbo, mn_sbo, mn_kadv;  // MN-major descriptor strides (bytes)
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma);
+    tma_prefetch_desc(&tmb);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int total_work = g.m_tiles * g.n_tiles * g.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % g.splits;
+        const int t = w / g.splits;
+        const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!g.a_mn) {
+            tma_load_2d(sa, &tma, &full_bar[stage], kb * BK, m_tile * BM);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BM / 64; ++b)
+              tma_load_2d(sa + b * (BK * 128), &tma, &full_bar[stage], m_tile * BM + b * 64, kb * BK);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(sb, &tmb, &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(sb + b * (BK * 128), &tmb, &full_bar[stage], n_tile * BN + b * 64, kb * BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % g.splits;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = g.a_mn ? make_smem_desc_sw128(sa + k * g.mn_kadv, g.mn_lbo, g.mn_sbo)
+                                       : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t db = g.b_mn ? make_smem_desc_sw128(sb + k * g.mn_kadv, g.mn_lbo, g.mn_sbo)
+                                       : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quarter owned by this warp
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int t = w / g.splits;
+      const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const long long row = (long long)m_tile * BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= g.N) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
+        tmem_wait_ld();
+        const bool full = (n0 + 32 <= g.N);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] * g.alpha;
+          if (g.bias != nullptr && (full || n0 + j < g.N)) x += __ldg(g.bias + n0 + j);
+          if (g.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (row_ok) {
+          if (g.mask != nullptr) {
+            const bf16* mp = g.mask + row * g.ld_mask + n0;
+            if (full && g.vecmask) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 mv = *reinterpret_cast<const uint4*>(mp + j * 8);
+                const bf16* mb = reinterpret_cast<const bf16*>(&mv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (!(__bfloat162float(mb[e]) > 0.f)) v[j * 8 + e] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N && !(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
+            }
+          }
+          if (g.c32 != nullptr) {
+            float* cp = g.c32 + row * g.ldc32 + n0;
+            if (g.atomic32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) atomicAdd(cp + j, v[j]);
+            } else if (full && g.vec32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(cp + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) cp[j] = v[j];
+            }
+          }
+          if (g.c16 != nullptr) {
+            bf16* cp = g.c16 + row * g.ldc16 + n0;
+            if (full && g.vec16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(cp + j * 8) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) cp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    TT_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = g.m_tiles * g.n_tiles * g.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+  TT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
+  TT_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", d.M, d.N, d.K);
+  TT_CHECK(d.A && d.B, "gemm: null operand");
+  TT_CHECK((d.lda % 8) == 0 && (d.ldb % 8) == 0, "gemm: operand pitches must be multiples of 8 elements (lda=%lld ldb=%lld)", d.lda, d.ldb);
+  TT_CHECK(((uintptr_t)d.A % 16) == 0 && ((uintptr_t)d.B % 16) == 0, "gemm: operands must be 16-byte aligned");
+  TT_CHECK(d.c32 || d.c16, "gemm: no output");
+
+  int BN = 64;
+  {  // largest tile with the least padded columns
+    long long best = -1;
+    const int cand[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
+      if (best < 0 || padded < best) { best = padded; BN = cand[i]; }
+    }
+  }
+  GemmArgs g;
+  g.M = (int)d.M; g.N = (int)d.N; g.K = (int)d.K;
+  g.a_mn = d.a_mn_major; g.b_mn = d.b_mn_major;
+  g.m_tiles = (int)((d.M + BM - 1) / BM);
+  g.n_tiles = (int)((d.N + BN - 1) / BN);
+  g.kb_total = (int)((d.K + BK - 1) / BK);
+  int splits = 1;
+  if (d.accumulate) {
+    splits = d.split_k;
+    if (splits <= 0) {
+      const int tiles = g.m_tiles * g.n_tiles;
+      splits = tiles >= num_sms() ? 1 : (num_sms() + tiles - 1) / tiles;
+    }
+    if (splits > g.kb_total) splits = g.kb_total;
+  }
+  g.kb_per_split = (g.kb_total + splits - 1) / splits;
+  g.splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.bias = d.bias; g.relu = d.relu;
+  g.mask = (const bf16*)d.relu_mask; g.ld_mask = d.ld_mask;
+  g.c32 = d.c32; g.ldc32 = d.ldc32; g.atomic32 = d.accumulate ? 1 : 0;
+  g.c16 = (bf16*)d.c16; g.ldc16 = d.ldc16;
+  g.alpha = d.alpha;
+  g.vec32 = d.c32 && (d.ldc32 % 4 == 0) && ((uintptr_t)d.c32 % 16 == 0);
+  g.vec16 = d.c16 && (d.ldc16 % 8 == 0) && ((uintptr_t)d.c16 % 16 == 0);
+  g.vecmask = d.relu_mask && (d.ld_mask % 8 == 0) && ((uintptr_t)d.relu_mask % 16 == 0);
+  g.mn_lbo = BK * 128; g.mn_sbo = 1024; g.mn_kadv = 2048;
+  if (const char* dbg = getenv("TT_DBG_MN")) {  // bring-up knob: "lbo,sbo,kadv"
+    sscanf(dbg, "%d,%d,%d", &g.mn_lbo, &g.mn_sbo, &g.mn_kadv);
+  }
+  TT_CHECK(!(d.accumulate && (d.bias || d.relu || d.relu_mask || d.c16)),
+           "gemm: split-K accumulation only supports a plain fp32 output");
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!d.a_mn_major) rc = make_tmap_bf16(&ta, d.A, d.K, d.M, d.lda, 64, BM);
+  else               rc = make_tmap_bf16(&ta, d.A, d.M, d.K, d.lda, 64, BK);
+  if (rc) return rc;
+  if (!d.b_mn_major) rc = make_tmap_bf16(&tb, d.B, d.K, d.N, d.ldb, 64, BN);
+  else               rc = make_tmap_bf16(&tb, d.B, d.N, d.K, d.ldb, 64, BK);
+  if (rc) return rc;
+
+  switch (BN) {
+    case 64:  return launch_gemm<64>(ta, tb, g, stream);
+    case 128: return launch_gemm<128>(ta, tb, g, stream);
+    default:  return launch_gemm<256>(ta, tb, g, stream);
+  }
+}
+
+}  // namespace tt

@@ -1,0 +1,70 @@
+// Internal C++ interfaces between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tt {
+
+struct GemmDesc {
+  const void* A = nullptr;  // bf16; [M,K] pitch lda, or [K,M] pitch lda when a_mn_major
+  long long lda = 0;
+  int a_mn_major = 0;
+  const void* B = nullptr;  // bf16; [N,K] pitch ldb, or [K,N] pitch ldb when b_mn_major
+  long long ldb = 0;
+  int b_mn_major = 0;
+  long long M = 0, N = 0, K = 0;
+  const float* bias = nullptr;  // [N]
+  int relu = 0;
+  const void* relu_mask = nullptr;  // bf16 [M, ld_mask]; output zeroed where mask <= 0
+  long long ld_mask = 0;
+  float* c32 = nullptr;
+  long long ldc32 = 0;
+  void* c16 = nullptr;  // bf16
+  long long ldc16 = 0;
+  int accumulate = 0;  // fp32 atomicAdd into c32 (split-K); c32 must be initialised by the caller
+  int split_k = 0;     // 0 = auto
+  float alpha = 1.f;
+};
+int gemm_bf16(const GemmDesc& d, cudaStream_t stream);
+
+// In-batch sampled-softmax cross entropy.
+size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d);
+int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
+                   long long target_offset, float* ce, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
+// dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].
+int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
+                   long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
+                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, void* ws, size_t ws_bytes,
+                   cudaStream_t stream);
+
+// MIPS: top-k of Q C^T per query row.
+size_t mips_workspace_bytes(long long Q, long long C, long long d, long long k);
+int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, const float* Q32, long long ldq32,
+              const float* C32, long long ldc32, long long nq, long long nc, long long d, long long k, long long* idx,
+              float* scores, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// Self-attention core for the history encoder (per sequence, per head).
+int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long long D, long long heads, void* out,
+             long long ldo, cudaStream_t stream);
+int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, long long nseq, long long H, long long D,
+             long long heads, void* dqkv, long long lddqkv, cudaStream_t stream);
+
+// Elementwise / gather / scatter helpers (elementwise.cu)
+int cast_rows_bf16(const float* src, long long rows, long long cols, long long ld_src, void* dst, long long ld_dst,
+                   long long dst_cols, cudaStream_t stream);
+int gather_rows_bf16(const float* table, long long table_rows, long long dim, const long long* ids, long long n,
+                     void* dst, long long ld_dst, int* oob_flag, cudaStream_t stream);
+int gather_rows_f32(const float* table, long long table_rows, long long dim, const long long* ids, long long n,
+                    float* dst, long long ld_dst, int* oob_flag, cudaStream_t stream);
+int scatter_add_rows(const void* src16, const float* src32, long long ld_src, const long long* ids, long long n,
+                     long long dim, float* table_grad, long long table_rows, cudaStream_t stream);
+int colsum(const void* src16, const float* src32, long long rows, long long cols, long long ld, float* out,
+           cudaStream_t stream);
+int history_gather_pool(const float* table, long long table_rows, long long D, const long long* ids, long long B,
+                        long long H, const float* pe, void* x16, long long ldx, float* mean, long long ldmean,
+                        int* oob_flag, cudaStream_t stream);
+int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, long long lddmean,
+                         const long long* ids, long long B, long long H, long long D, float* table_grad,
+                         long long table_rows, cudaStream_t stream);
+
+}  // namespace tt
