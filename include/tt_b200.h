@@ -32,6 +32,8 @@ int tt_abi_version(void);
 const char* tt_last_error(void);
 /* Number of SMs of the current device (148 on B200); negative on error. */
 int tt_device_sm_count(void);
+/* Total number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+long long tt_launch_count(void);
 
 /* ---- data movement (HBM-bound helpers) ------------------------------------------------------ */
 

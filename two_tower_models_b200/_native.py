@@ -22,6 +22,7 @@ SIGNATURES = {
     "tt_abi_version": (I32, []),
     "tt_last_error": (c_char_p, []),
     "tt_device_sm_count": (I32, []),
+    "tt_launch_count": (I64, []),
     "tt_cast_rows_bf16": (I32, [P, I64, I64, I64, P, I64, I64, P]),
     "tt_gather_rows_bf16": (I32, [P, I64, I64, P, I64, P, I64, P, P]),
     "tt_gather_rows_f32": (I32, [P, I64, I64, P, I64, P, I64, P, P]),

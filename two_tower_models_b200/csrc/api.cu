@@ -1,5 +1,6 @@
 // C ABI (include/tt_b200.h) over the kernel translation units + shared host utilities.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "../../include/tt_b200.h"
@@ -16,6 +17,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached = 0;
@@ -71,6 +75,8 @@ extern "C" {
 
 int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
 const char* tt_last_error(void) { return g_err; }
+
+long long tt_launch_count(void) { return (long long)g_launches.load(); }
 
 int tt_device_sm_count(void) {
   int dev = 0, n = 0;

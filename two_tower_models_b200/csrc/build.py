@@ -51,7 +51,8 @@ def build(force=False, verbose=False):
         results = list(ex.map(compile_one, srcs))
     log = []
     for src, obj, r in results:
-        log.append(f"== {os.path.basename(src)}\n{r.stderr}")
+        err = "\n".join(l for l in r.stderr.splitlines() if "Compile time" not in l)
+        log.append(f"== {os.path.basename(src)}\n{err}")
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"nvcc failed on {src}")

@@ -295,6 +295,7 @@ static int launch_ce_fwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeF
   }
   ce_fwd_kernel<DP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -327,6 +328,7 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
   if (rc) return rc;
   ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, a.diag, ce, lse);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -632,6 +634,7 @@ static int launch_ce_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeB
   }
   ce_bwd_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -659,6 +662,7 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   ce_bwd_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)xr, (int)d, DP, s.T, s.CT, a.partial,
                                                                          a.slot_stride, out32, ld32, (bf16*)out16, ld16);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

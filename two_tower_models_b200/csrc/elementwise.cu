@@ -36,6 +36,7 @@ int cast_rows_bf16(const float* src, long long rows, long long cols, long long l
   const long long n = rows * ((dst_cols + 1) / 2);
   cast_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, rows, (int)cols, ld_src, (bf16*)dst, ld_dst, (int)dst_cols);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -68,6 +69,7 @@ int gather_rows_bf16(const float* table, long long table_rows, long long dim, co
   TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_bf16: bad shape");
   gather_rows_kernel<bf16><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, (bf16*)dst, ld_dst, oob_flag);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 int gather_rows_f32(const float* table, long long table_rows, long long dim, const long long* ids, long long n,
@@ -76,6 +78,7 @@ int gather_rows_f32(const float* table, long long table_rows, long long dim, con
   TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_f32: bad shape");
   gather_rows_kernel<float><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, dst, ld_dst, oob_flag);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -103,6 +106,7 @@ int scatter_add_rows(const void* src16, const float* src32, long long ld_src, co
   TT_CHECK((src16 != nullptr) != (src32 != nullptr), "scatter_add_rows: exactly one source");
   scatter_add_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -136,6 +140,7 @@ int colsum(const void* src16, const float* src32, long long rows, long long cols
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
   colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)src16, src32, rows, (int)cols, ld, out, rpb);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -173,6 +178,7 @@ int history_gather_pool(const float* table, long long table_rows, long long D, c
   const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
   history_gather_pool_kernel<<<(unsigned)B, threads, 0, stream>>>(table, table_rows, (int)D, ids, (int)H, pe, (bf16*)x16, ldx, mean, ldmean, oob_flag);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -199,6 +205,7 @@ int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, l
   const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
   history_scatter_grad_kernel<<<(unsigned)B, threads, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, (int)H, (int)D, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -259,6 +259,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   const int grid = total < num_sms() ? total : num_sms();
   gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
   TT_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
