@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py - user-item pairs/sec through TwoTowerBaseRetrieval.train_forward (+ backward) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d 128] [--batch 8192]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): TwoTowerBaseRetrieval, d = DU = DI = 128, F = IU = II = 128,
+per-GPU batch 8192, hash tables 100 000 rows, T = 1, user_value_weights = [1.0]; synthetic seeded inputs,
+reference default initialisation under torch.manual_seed(0).  One step = train_forward + loss.backward()
+over one batch (8192 pairs per GPU).  N > 1: the batch is sharded (8192 rows per rank, weak scaling); item
+embeddings are all-gathered so every rank scores its users against the global batch of negatives, dV is
+reduce-scattered back and dense gradients are all-reduced (two_tower_models_b200/distributed.py).
+
+`value`  : pairs/s with the step's inputs already resident in HBM (a ring of batches larger than L2).
+`e2e`    : pairs/s through the public module API from pinned HOST buffers: H2D of the 7 input tensors and
+           a D2H read of the loss inside the timed region, every step.
+`--impl reference` : the reference's CPU path (the oracle port of it, oracle/two_tower_oracle.py, the
+           reference itself is not present on the GPU box) on all host cores, same config and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HASH = 100_000
+RING = 32  # distinct input batches cycled through: 32 x ~8.5 MB = 272 MB > 126 MB L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=8192, help="rows per GPU")
+    ap.add_argument("--features", type=int, default=128)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_batch(B, F, gen):
+    return dict(
+        user_id=torch.randint(0, HASH, (B,), generator=gen),
+        user_features=torch.randn(B, F, generator=gen),
+        user_history=torch.randint(0, HASH, (B, 8), generator=gen),
+        item_id=torch.randint(0, HASH, (B,), generator=gen),
+        item_features=torch.randn(B, F, generator=gen),
+        position=torch.randint(0, 100, (B,), generator=gen),
+        labels=torch.randint(0, 2, (B, 1), generator=gen).float(),
+    )
+
+
+ORDER = ["user_id", "user_features", "user_history", "item_id", "item_features", "position", "labels"]
+
+
+def batch_bytes(b):
+    return sum(t.numel() * t.element_size() for t in b.values())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # under load = samples in the upper half (the sampler also sees idle gaps around the region)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path (oracle port), all host threads, same config / metric."""
+    if rank != 0:
+        return
+    import oracle
+
+    torch.set_num_threads(os.cpu_count())
+    B, d, F = args.batch, args.d, args.features
+    params, uvw = oracle_params(d, F)
+    gen = torch.Generator().manual_seed(1)
+    batches = [make_batch(B, F, gen) for _ in range(2)]
+    for i in range(max(1, min(args.warmup, 2))):
+        oracle.base_train_forward_with_grads(params, uvw, batches[i % 2])
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle.base_train_forward_with_grads(params, uvw, batches[i % 2])
+    dt = (time.perf_counter() - t0) / steps
+    val = B / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "user-item pairs/sec through train_forward (fwd+bwd)", "value": val,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} full steps of B={B} (oracle port of the reference CPU path, fp32, autograd backward)"},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"TwoTowerBaseRetrieval.train_forward+backward d={args.d} F={args.features} batch={args.batch}/GPU "
+                    f"hash={HASH} T=1 (BASELINE configs[1])",
+        "global_batch": args.batch * world, "d": args.d, "parallelism": f"dp{world}" if world > 1 else "single",
+        "negatives": "in-batch, all-gathered over NCCL" if world > 1 else "in-batch",
+        "l2": f"input ring of {RING} batches > 126 MB L2",
+    }
+
+
+def oracle_params(d, F):
+    """Reference-default-initialised parameters (seed 0) as a state_dict; built from torch.nn hosts."""
+    import two_tower_models_b200 as tt
+
+    torch.manual_seed(0)
+    m = tt.TwoTowerBaseRetrieval(100, HASH, d, F, HASH, d, F, [1.0], tt.BaselineMIPSModule(16, d))
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}, torch.tensor([1.0])
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import two_tower_models_b200 as tt
+    from two_tower_models_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, d, F = args.batch, args.d, args.features
+    K, W = args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = tt.TwoTowerBaseRetrieval(100, HASH, d, F, HASH, d, F, [1.0], tt.BaselineMIPSModule(16, d)).to(dev)
+    if world > 1:
+        from two_tower_models_b200 import distributed as ttd
+
+        ttd.enable_data_parallel(model)
+
+    gen = torch.Generator().manual_seed(1 + rank)
+    host_ring = [{k: v.pin_memory() for k, v in make_batch(B, F, gen).items()} for _ in range(RING)]
+    dev_ring = [{k: v.to(dev) for k, v in b.items()} for b in host_ring]
+    in_bytes = batch_bytes(host_ring[0])
+
+    def step(b):
+        model.zero_grad(set_to_none=True)
+        loss = model.train_forward(*[b[k] for k in ORDER])
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(W):
+        step(dev_ring[i % RING])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.TIMER = ops.KernelTimer()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        loss = step(dev_ring[(W + i) % RING])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    spans = ops.TIMER.totals_ms()
+    ops.TIMER = None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = B * world / (ms_step * 1e-3)
+    loss_val = float(loss.item())
+
+    # ---------------- end to end from pinned host buffers (`e2e`) ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host_ring[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(K + W, dtype=torch.float32).pin_memory()
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for k in ORDER:
+                slots[s][k].copy_(host_ring[i % RING][k], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_steps(n0, n):
+        cur = torch.cuda.current_stream()
+        upload(n0)
+        for i in range(n0, n0 + n):
+            if i + 1 < n0 + n:
+                upload(i + 1)  # prefetch the next batch while this one computes
+            s = i % 2
+            cur.wait_event(ready[s])
+            l = step(slots[s])
+            freed[s].record(cur)
+            loss_host[i].copy_(l.detach(), non_blocking=True)  # D2H read of the step's result
+
+    for s in range(2):
+        freed[s].record(torch.cuda.current_stream())
+    e2e_steps(0, W)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_steps(W, K)
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[1].item()) / K  # host wall clock between the syncs: includes every copy and launch
+    e2e_value = B * world / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (B x N scoring) ----------------
+    pk, pk_src = peaks()
+    N = B * world
+    kern = {}
+    for name, flops in (("inbatch_ce_fwd", 2.0 * B * N * d), ("inbatch_ce_bwd", 4.0 * B * N * d)):
+        if name in spans and spans[name][1] > 0:
+            tot, cnt = spans[name]
+            per = tot / cnt
+            kern[name] = {"ms": per, "tflops": flops / (per * 1e-3) / 1e12, "calls": cnt}
+    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    roofline = None
+    if dom:
+        roofline = {
+            "bound": "tensor", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": kern[dom]["tflops"] / peak_tf, "traffic": None,
+            "peak_source": f"{pk_src} (sustained cuBLAS bf16; the kernel is timed inside a long step)",
+            "flops_per_launch": 4.0 * B * N * d if dom == "inbatch_ce_bwd" else 2.0 * B * N * d,
+            "kernels": kern,
+            "scoring_fraction_of_step": sum(v["ms"] for v in kern.values()) / ms_step,
+        }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        torch.set_num_threads(os.cpu_count())
+        params, uvw = oracle_params(d, F)
+        hb = {k: v.clone() for k, v in host_ring[0].items()}
+        oracle.base_train_forward_with_grads(params, uvw, hb)
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            ref_loss, _ = oracle.base_train_forward_with_grads(params, uvw, hb)
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": B / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} full steps of B={B} on the host (oracle port of the reference CPU path, fp32)",
+               "ms_per_step": dt * 1e3}
+
+    out = {
+        "metric": "user-item pairs/sec through train_forward (fwd+bwd)", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "loss": loss_val,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

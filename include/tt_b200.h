@@ -91,6 +91,21 @@ int tt_inbatch_ce_bwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64
                       void* dU_bf16, int64_t lddu16, float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- brute-force MIPS ------------------------------------------------------------------------ */
+
+/* Scratch bytes needed by tt_mips_topk for this shape on the current device. */
+int64_t tt_mips_workspace_bytes(int64_t nq, int64_t nc, int64_t d, int64_t k);
+
+/* idx[q, 0:k], scores[q, 0:k] = top-k of Q C^T per query row, scores descending, exact ties by ascending
+ * corpus index.  Replaces torch.topk(torch.matmul(query, corpus.T), k) (reference
+ * src/baseline_mips_module.py:57-61).  Q_bf16 [nq,d] / C_bf16 [nc,d] are bf16 copies used to screen the
+ * corpus on the tensor cores (no [nq,nc] matrix is materialised); the best k + margin candidates are then
+ * re-scored in fp32 from Q_f32 / C_f32, which defines the returned scores and order.
+ * d <= 128, k <= 224, nc < 2^32 - 1. */
+int tt_mips_topk(const void* Q_bf16, int64_t ldq16, const void* C_bf16, int64_t ldc16, const float* Q_f32,
+                 int64_t ldq32, const float* C_f32, int64_t ldc32, int64_t nq, int64_t nc, int64_t d, int64_t k,
+                 int64_t* idx, float* scores, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- history encoder helpers ---------------------------------------------------------------- */
 
 /* x_bf16[b*H+h, :] = bf16(table[ids[b,h]] + pe[h]) (pe may be NULL);  mean[b, :] = mean_h table[ids[b,h]].
@@ -101,6 +116,18 @@ int tt_history_gather_pool(const float* table, int64_t table_rows, int64_t D, co
 /* table_grad[ids[b,h], :] += dx_bf16[b*H+h, :] + dmean[b, :] / H   (either source may be NULL). */
 int tt_history_scatter_grad(const void* dx_bf16, int64_t lddx, const float* dmean, int64_t lddmean, const int64_t* ids,
                             int64_t B, int64_t H, int64_t D, float* table_grad, int64_t table_rows, void* stream);
+
+/* Self-attention core of nn.MultiheadAttention (reference src/user_history_encoder.py:60-67, 103-108;
+ * torch.nn.functional.multi_head_attention_forward): per sequence and head,
+ * out = softmax(q k^T / sqrt(D/heads)) v, no mask, no dropout.  qkv_bf16: [nseq*H, ldqkv] rows = [q | k | v]
+ * (3D columns, head h in columns [h*D/heads, (h+1)*D/heads) of each block), i.e. the output of the packed
+ * in-projection.  Only the first q_rows query rows of every sequence are produced: out_bf16 is
+ * [nseq*q_rows, ldo] (the encoder consumes row 0 of its last layer only, reference :116). */
+int tt_attn_fwd(const void* qkv_bf16, int64_t ldqkv, int64_t nseq, int64_t H, int64_t D, int64_t heads, int64_t q_rows,
+                void* out_bf16, int64_t ldo, void* stream);
+/* dqkv_bf16 [nseq*H, lddqkv] from dout_bf16 [nseq*q_rows, lddo] (softmax recomputed from qkv). */
+int tt_attn_bwd(const void* qkv_bf16, int64_t ldqkv, const void* dout_bf16, int64_t lddo, int64_t nseq, int64_t H,
+                int64_t D, int64_t heads, int64_t q_rows, void* dqkv_bf16, int64_t lddqkv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,13 +5,14 @@ Same class names, constructor arguments, methods and state_dict keys as the refe
 include/tt_b200.h (libtt_b200.so).  CUDA only - there is no CPU fallback.
 """
 from . import _native, ops  # noqa: F401
+from .history import UserHistoryEncoder  # noqa: F401
+from .mips import BaselineMIPSModule  # noqa: F401
+from .towers import TwoTowerBaseRetrieval, TwoTowerWithUserHistoryEncoder  # noqa: F401
 
-__all__ = ["ops"]
-try:
-    from .history import UserHistoryEncoder  # noqa: F401
-    from .mips import BaselineMIPSModule  # noqa: F401
-    from .towers import TwoTowerBaseRetrieval, TwoTowerWithUserHistoryEncoder  # noqa: F401
-
-    __all__ += ["BaselineMIPSModule", "TwoTowerBaseRetrieval", "TwoTowerWithUserHistoryEncoder", "UserHistoryEncoder"]
-except ModuleNotFoundError:  # modules land incrementally during bring-up
-    pass
+__all__ = [
+    "ops",
+    "BaselineMIPSModule",
+    "TwoTowerBaseRetrieval",
+    "TwoTowerWithUserHistoryEncoder",
+    "UserHistoryEncoder",
+]

@@ -32,8 +32,12 @@ SIGNATURES = {
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, I64, P]),
+    "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
+    "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_history_gather_pool": (I32, [P, I64, I64, P, I64, I64, P, P, I64, P, I64, P, P]),
     "tt_history_scatter_grad": (I32, [P, I64, P, I64, P, I64, I64, I64, P, I64, P]),
+    "tt_attn_fwd": (I32, [P, I64, I64, I64, I64, I64, I64, P, I64, P]),
+    "tt_attn_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, I64, P, I64, P]),
 }
 
 

@@ -135,6 +135,16 @@ int tt_inbatch_ce_bwd(const void* U, int64_t ldu, const void* V, int64_t ldv, in
                         ws, (size_t)ws_bytes, S(stream));
 }
 
+int64_t tt_mips_workspace_bytes(int64_t nq, int64_t nc, int64_t d, int64_t k) {
+  return (int64_t)mips_workspace_bytes(nq, nc, d, k);
+}
+int tt_mips_topk(const void* Q16, int64_t ldq16, const void* C16, int64_t ldc16, const float* Q32, int64_t ldq32,
+                 const float* C32, int64_t ldc32, int64_t nq, int64_t nc, int64_t d, int64_t k, int64_t* idx,
+                 float* scores, void* ws, int64_t ws_bytes, void* stream) {
+  return mips_topk(Q16, ldq16, C16, ldc16, Q32, ldq32, C32, ldc32, nq, nc, d, k, (long long*)idx, scores, ws,
+                   (size_t)ws_bytes, S(stream));
+}
+
 int tt_history_gather_pool(const float* table, int64_t table_rows, int64_t D, const int64_t* ids, int64_t B, int64_t H,
                            const float* pe, void* x16, int64_t ldx, float* mean, int64_t ldmean, int32_t* oob_flag,
                            void* stream) {
@@ -143,6 +153,15 @@ int tt_history_gather_pool(const float* table, int64_t table_rows, int64_t D, co
 int tt_history_scatter_grad(const void* dx16, int64_t lddx, const float* dmean, int64_t lddmean, const int64_t* ids,
                             int64_t B, int64_t H, int64_t D, float* table_grad, int64_t table_rows, void* stream) {
   return history_scatter_grad(dx16, lddx, dmean, lddmean, (const long long*)ids, B, H, D, table_grad, table_rows, S(stream));
+}
+
+int tt_attn_fwd(const void* qkv, int64_t ldqkv, int64_t nseq, int64_t H, int64_t D, int64_t heads, int64_t q_rows,
+                void* out, int64_t ldo, void* stream) {
+  return attn_fwd(qkv, ldqkv, nseq, H, D, heads, q_rows, out, ldo, S(stream));
+}
+int tt_attn_bwd(const void* qkv, int64_t ldqkv, const void* dout, int64_t lddo, int64_t nseq, int64_t H, int64_t D,
+                int64_t heads, int64_t q_rows, void* dqkv, int64_t lddqkv, void* stream) {
+  return attn_bwd(qkv, ldqkv, dout, lddo, nseq, H, D, heads, q_rows, dqkv, lddqkv, S(stream));
 }
 
 }  // extern "C"

@@ -43,11 +43,12 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
               const float* C32, long long ldc32, long long nq, long long nc, long long d, long long k, long long* idx,
               float* scores, void* ws, size_t ws_bytes, cudaStream_t stream);
 
-// Self-attention core for the history encoder (per sequence, per head).
-int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long long D, long long heads, void* out,
-             long long ldo, cudaStream_t stream);
+// Self-attention core for the history encoder (per sequence, per head); qkv rows = [q | k | v] of width 3D.
+// Only the first q_rows query rows of every sequence are computed (out / dout are [nseq*q_rows, D]).
+int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long long D, long long heads, long long q_rows,
+             void* out, long long ldo, cudaStream_t stream);
 int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, long long nseq, long long H, long long D,
-             long long heads, void* dqkv, long long lddqkv, cudaStream_t stream);
+             long long heads, long long q_rows, void* dqkv, long long lddqkv, cudaStream_t stream);
 
 // Elementwise / gather / scatter helpers (elementwise.cu)
 int cast_rows_bf16(const float* src, long long rows, long long cols, long long ld_src, void* dst, long long ld_dst,

@@ -17,6 +17,50 @@ _BF16 = torch.bfloat16
 _CHECK_IDS = os.environ.get("TT_B200_CHECK_IDS", "0") == "1"
 
 
+class KernelTimer:
+    """Optional CUDA-event spans around named native calls (bench.py's per-kernel roofline numbers).
+
+    Events are recorded on the launching (current) stream, so the spans measure device time of exactly
+    the kernels enqueued inside them.  Disabled (None) by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.spans = {}
+
+    def begin(self, name):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        self.spans.setdefault(name, []).append((e0, e1))
+        return e1
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.spans.items()}
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+class _span:
+    def __init__(self, name):
+        self.name = name
+        self.e1 = None
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.e1 = TIMER.begin(self.name)
+
+    def __exit__(self, *exc):
+        if self.e1 is not None:
+            self.e1.record(torch.cuda.current_stream())
+        return False
+
+
+def launch_count() -> int:
+    """Kernels launched by libtt_b200.so in this process so far."""
+    return int(_native.lib().tt_launch_count())
+
+
 def _r8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -130,6 +174,15 @@ def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, col_o
                                   out.data_ptr() + 4 * col_offset, out.stride(0), flag.data_ptr(), _stream())
     _native.check(rc, "gather_rows")
     _maybe_check_ids(table.device, "gather_rows")
+
+
+def gather_rows_new(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """fp32 table[ids] as a fresh [n, dim] tensor."""
+    _need_cuda(table, ids)
+    ids = _i64c(ids).reshape(-1)
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+    gather_rows(_f32c(table), ids, out)
+    return out
 
 
 def scatter_add_rows(src: torch.Tensor, ids: torch.Tensor, dim: int, table_rows: int, col_offset: int = 0,
@@ -379,11 +432,13 @@ def inbatch_ce_forward_raw(U16, V16, B, N, d, target_offset=0):
     ce = torch.empty(B, dtype=torch.float32, device=U16.device)
     lse = torch.empty(B, dtype=torch.float32, device=U16.device)
     ws = _ce_workspace(B, N, d, U16.device)
-    _native.check(
-        _native.lib().tt_inbatch_ce_fwd(U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d,
-                                        target_offset, ce.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-        "inbatch_ce_fwd",
-    )
+    with _span("inbatch_ce_fwd"):
+        _native.check(
+            _native.lib().tt_inbatch_ce_fwd(U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d,
+                                            target_offset, ce.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            _stream()),
+            "inbatch_ce_fwd",
+        )
     return ce, lse
 
 
@@ -394,14 +449,15 @@ def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=
     dU16 = torch.empty((B, _r8(d)), dtype=_BF16, device=dev) if want_bf16 else None
     dV16 = torch.empty((N, _r8(d)), dtype=_BF16, device=dev) if want_bf16 else None
     ws = _ce_workspace(B, N, d, dev)
-    _native.check(
-        _native.lib().tt_inbatch_ce_bwd(
-            U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, target_offset,
-            lse.data_ptr(), g.data_ptr(), dU.data_ptr(), dU.stride(0), _ptr(dU16), dU16.stride(0) if want_bf16 else 0,
-            dV.data_ptr(), dV.stride(0), _ptr(dV16), dV16.stride(0) if want_bf16 else 0,
-            ws.data_ptr(), ws.numel(), _stream()),
-        "inbatch_ce_bwd",
-    )
+    with _span("inbatch_ce_bwd"):
+        _native.check(
+            _native.lib().tt_inbatch_ce_bwd(
+                U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, target_offset,
+                lse.data_ptr(), g.data_ptr(), dU.data_ptr(), dU.stride(0), _ptr(dU16),
+                dU16.stride(0) if want_bf16 else 0, dV.data_ptr(), dV.stride(0), _ptr(dV16),
+                dV16.stride(0) if want_bf16 else 0, ws.data_ptr(), ws.numel(), _stream()),
+            "inbatch_ce_bwd",
+        )
     return dU, dV, dU16, dV16
 
 
@@ -438,3 +494,165 @@ class InBatchCEFunction(torch.autograd.Function):
 
 def inbatch_cross_entropy(U: torch.Tensor, V: torch.Tensor, target_offset: int = 0) -> torch.Tensor:
     return InBatchCEFunction.apply(U, V, target_offset)
+
+
+# --------------------------------------------------------------------------------------------
+# brute-force MIPS   (reference src/baseline_mips_module.py:57-72)
+# --------------------------------------------------------------------------------------------
+_mips_ws = {}
+
+
+def mips_topk(query: torch.Tensor, corpus: torch.Tensor, corpus16: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(indices int64 [Q,k], scores fp32 [Q,k]) = top-k of query @ corpus^T, scores descending."""
+    _need_cuda(query, corpus, corpus16)
+    q32 = _f32c(query.detach())
+    c32 = _f32c(corpus)
+    nq, d = q32.shape
+    nc = c32.shape[0]
+    q16 = getattr(query, "_tt_bf16", None)
+    if q16 is None:
+        q16 = cast_rows_bf16(q32)
+    L = _native.lib()
+    nbytes = int(L.tt_mips_workspace_bytes(nq, nc, d, k))
+    key = (str(q32.device), nbytes)
+    ws = _mips_ws.get(key)
+    if ws is None:
+        _mips_ws.clear()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=q32.device)
+        _mips_ws[key] = ws
+    idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
+    scores = torch.empty((nq, k), dtype=torch.float32, device=q32.device)
+    with _span("mips_topk"):
+        _native.check(
+            L.tt_mips_topk(q16.data_ptr(), q16.stride(0), corpus16.data_ptr(), corpus16.stride(0), q32.data_ptr(),
+                           q32.stride(0), c32.data_ptr(), c32.stride(0), nq, nc, d, k, idx.data_ptr(),
+                           scores.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+            "mips_topk",
+        )
+    return idx, scores
+
+
+# --------------------------------------------------------------------------------------------
+# history encoder   (reference src/user_history_encoder.py:80-121)
+# --------------------------------------------------------------------------------------------
+def attn_forward(qkv16: torch.Tensor, nseq: int, H: int, D: int, heads: int, q_rows: int) -> torch.Tensor:
+    out = torch.empty((nseq * q_rows, _r8(D)), dtype=_BF16, device=qkv16.device)
+    with _span("attn_fwd"):
+        _native.check(
+            _native.lib().tt_attn_fwd(qkv16.data_ptr(), qkv16.stride(0), nseq, H, D, heads, q_rows, out.data_ptr(),
+                                      out.stride(0), _stream()),
+            "attn_fwd",
+        )
+    return out
+
+
+def attn_backward(qkv16: torch.Tensor, dout16: torch.Tensor, nseq: int, H: int, D: int, heads: int,
+                  q_rows: int) -> torch.Tensor:
+    dqkv = torch.empty((nseq * H, qkv16.shape[1]), dtype=_BF16, device=qkv16.device)
+    with _span("attn_bwd"):
+        _native.check(
+            _native.lib().tt_attn_bwd(qkv16.data_ptr(), qkv16.stride(0), dout16.data_ptr(), dout16.stride(0), nseq, H, D,
+                                      heads, q_rows, dqkv.data_ptr(), dqkv.stride(0), _stream()),
+            "attn_bwd",
+        )
+    return dqkv
+
+
+class HistoryEncoderFunction(torch.autograd.Function):
+    """summary[B, 2D] = [attention output of history row 0 | mean-pooled history].
+
+    Two entry forms:  (ids int64 [B,H], table fp32 [rows, D])  - the embedding lookup is folded into the
+    first kernel (TwoTowerWithUserHistoryEncoder), or  (None, x fp32 [B,H,D])  - UserHistoryEncoder.forward.
+    Per layer: packed in-projection (tcgen05 GEMM + bias) -> per-head softmax(QK^T)V -> out-projection
+    (GEMM + bias); no residual / LayerNorm / FFN, as in the reference.  The last layer only evaluates
+    query row 0 of every sequence (the only row the reference consumes, :116).
+    """
+
+    @staticmethod
+    def forward(ctx, ids, table_or_x, pe, heads: int, packed: PackedWeights, tag: str, *params):
+        src = table_or_x
+        _need_cuda(src, ids, pe)
+        if ids is None:
+            B, H, D = src.shape
+            table = _f32c(src).reshape(B * H, D)
+            ids_ = torch.arange(B * H, dtype=torch.int64, device=src.device).reshape(B, H)
+        else:
+            table = _f32c(src)
+            ids_ = _i64c(ids)
+            B, H = ids_.shape
+            D = table.shape[1]
+        L = len(params) // 4
+        dev = table.device
+        lib = _native.lib()
+        D8, Q8 = _r8(D), _r8(3 * D)
+        x16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
+        summary = torch.empty((B, 2 * D), dtype=torch.float32, device=dev)
+        flag = _oob_flag(dev)
+        pe_ = None if pe is None else _f32c(pe)
+        _native.check(
+            lib.tt_history_gather_pool(table.data_ptr(), table.shape[0], D, ids_.data_ptr(), B, H, _ptr(pe_),
+                                       x16.data_ptr(), x16.stride(0), summary.data_ptr() + 4 * D, summary.stride(0),
+                                       flag.data_ptr(), _stream()),
+            "history_gather_pool",
+        )
+        _maybe_check_ids(dev, "history lookup")
+        saved = []
+        recent = summary[:, :D]
+        for l in range(L):
+            in_w, in_b, out_w, out_b = params[4 * l: 4 * l + 4]
+            last = l == L - 1
+            q_rows = 1 if last else H
+            in_w16 = packed.get(f"{tag}.{l}.in", in_w)
+            out_w16 = packed.get(f"{tag}.{l}.out", out_w)
+            qkv16 = torch.empty((B * H, Q8), dtype=_BF16, device=dev)
+            gemm(x16, in_w16, B * H, 3 * D, D, bias=_f32c(in_b), out16=qkv16)
+            o16 = attn_forward(qkv16, B, H, D, heads, q_rows)
+            saved += [x16, qkv16, o16, in_w16, out_w16]
+            if last:
+                gemm(o16, out_w16, B, D, D, bias=_f32c(out_b), out32=recent)
+            else:
+                y16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
+                gemm(o16, out_w16, B * H, D, D, bias=_f32c(out_b), out16=y16)
+                x16 = y16
+        ctx.save_for_backward(ids_, *saved)
+        ctx.dims = (B, H, D, heads, L, table.shape[0], ids is None, tuple(src.shape))
+        return summary
+
+    @staticmethod
+    def backward(ctx, dsummary):
+        ids_, *saved = ctx.saved_tensors
+        B, H, D, heads, L, table_rows, dense_x, src_shape = ctx.dims
+        dev = dsummary.device
+        lib = _native.lib()
+        D8 = _r8(D)
+        ds = _f32c(dsummary)
+        dy16 = cast_rows_bf16(ds, cols=D)  # gradient of the last layer's row-0 output, [B, D8]
+        dmean = ds[:, D:]
+        grads = [None] * (4 * L)
+        for l in range(L - 1, -1, -1):
+            x16, qkv16, o16, in_w16, out_w16 = saved[5 * l: 5 * l + 5]
+            last = l == L - 1
+            q_rows = 1 if last else H
+            rows = B * q_rows
+            d_out_w = torch.zeros((D, D), dtype=torch.float32, device=dev)
+            gemm(dy16, o16, D, D, rows, a_mn=True, b_mn=True, out32=d_out_w, accumulate=True)
+            d_out_b = colsum(dy16, D)
+            do16 = torch.empty((rows, D8), dtype=_BF16, device=dev)
+            gemm(dy16, out_w16, rows, D, D, b_mn=True, out16=do16)
+            dqkv16 = attn_backward(qkv16, do16, B, H, D, heads, q_rows)
+            d_in_w = torch.zeros((3 * D, D), dtype=torch.float32, device=dev)
+            gemm(dqkv16, x16, 3 * D, D, B * H, a_mn=True, b_mn=True, out32=d_in_w, accumulate=True)
+            d_in_b = colsum(dqkv16, 3 * D)
+            dx16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
+            gemm(dqkv16, in_w16, B * H, D, 3 * D, b_mn=True, out16=dx16)
+            grads[4 * l: 4 * l + 4] = [d_in_w, d_in_b, d_out_w, d_out_b]
+            dy16 = dx16
+        dtable = torch.zeros((table_rows, D), dtype=torch.float32, device=dev)
+        _native.check(
+            lib.tt_history_scatter_grad(dy16.data_ptr(), dy16.stride(0), dmean.data_ptr(), dmean.stride(0),
+                                        ids_.data_ptr(), B, H, D, dtable.data_ptr(), table_rows, _stream()),
+            "history_scatter_grad",
+        )
+        if dense_x:
+            dtable = dtable.reshape(src_shape)
+        return (None, dtable, None, None, None, None, *grads)

@@ -166,3 +166,69 @@ class TwoTowerBaseRetrieval(nn.Module):
         return self.compute_training_loss(
             user_embedding=user_embedding, item_embeddings=item_embeddings, position=position, labels=labels
         )
+
+
+class TwoTowerWithUserHistoryEncoder(TwoTowerBaseRetrieval):
+    """Base model + `UserHistoryEncoder` over the user's item history
+    (reference src/two_tower_with_user_history_encoder.py:14-122).
+
+    History ids are looked up in the ITEM id table (:105), summarised to [B, 2*DI] and appended to
+    the user tower input, whose Linear therefore takes 2*DU + 2*DI inputs (:81-83).  The reference
+    hard-codes 4 heads / 3 layers (:64-70); they are exposed here as optional trailing kwargs with
+    those defaults (BASELINE config 3 uses 2 layers).
+    """
+
+    def __init__(
+        self,
+        num_items: int,
+        user_id_hash_size: int,
+        user_id_embedding_dim: int,
+        user_features_size: int,
+        user_history_seqlen: int,
+        item_id_hash_size: int,
+        item_id_embedding_dim: int,
+        item_features_size: int,
+        user_value_weights: List[float],
+        mips_module: nn.Module,
+        num_attention_heads: int = 4,
+        num_attention_layers: int = 3,
+    ) -> None:
+        super().__init__(
+            num_items=num_items,
+            user_id_hash_size=user_id_hash_size,
+            user_id_embedding_dim=user_id_embedding_dim,
+            user_features_size=user_features_size,
+            item_id_hash_size=item_id_hash_size,
+            item_id_embedding_dim=item_id_embedding_dim,
+            item_features_size=item_features_size,
+            user_value_weights=user_value_weights,
+            mips_module=mips_module,
+        )
+        from .history import UserHistoryEncoder
+
+        self.user_history_encoder = UserHistoryEncoder(
+            item_id_embedding_dim=item_id_embedding_dim,
+            history_len=user_history_seqlen,
+            num_attention_heads=num_attention_heads,
+            num_attention_layers=num_attention_layers,
+            use_positional_encoding=True,
+        )
+        self.user_tower_arch = nn.Linear(
+            2 * user_id_embedding_dim + self.user_history_encoder.get_output_dim(), item_id_embedding_dim
+        )
+
+    def _user_tower_extra(self, user_history: torch.Tensor) -> Optional[torch.Tensor]:
+        """[B, 2*DI] = [attention output of the newest item | mean-pooled history] (gather fused in)."""
+        return self.user_history_encoder.encode_ids(self.item_id_embedding_arch.weight, user_history)
+
+    def process_user_features(
+        self, user_id: torch.Tensor, user_features: torch.Tensor, user_history: torch.Tensor
+    ) -> torch.Tensor:
+        """[B, 2*DU + 2*DI] = cat(id emb, feature MLP, most-recent attention row, mean-pool) (reference :85-122)."""
+        user_tower_input = super().process_user_features(
+            user_id=user_id, user_features=user_features, user_history=user_history
+        )
+        return torch.cat([user_tower_input, self._user_tower_extra(user_history)], dim=1)
+
+
+TwoTowerWithUserHistoryEncoder._tt_fused_process_user_features = TwoTowerWithUserHistoryEncoder.process_user_features
