@@ -160,6 +160,7 @@ def workload_config(args, world):
         "global_batch": args.batch * world, "d": args.d, "parallelism": f"dp{world}" if world > 1 else "single",
         "negatives": "in-batch, all-gathered over NCCL" if world > 1 else "in-batch",
         "l2": f"input ring of {RING} batches > 126 MB L2",
+        "step": "train_forward + loss.backward(), gradients of all 14 parameter tensors, weights re-cast to bf16 every step",
     }
 
 
@@ -204,11 +205,33 @@ def main():
     dev_ring = [{k: v.to(dev) for k, v in b.items()} for b in host_ring]
     in_bytes = batch_bytes(host_ring[0])
 
-    def step(b):
+    sync = model._dp.sync_gradients if world > 1 else None
+    use_graph = not args.no_graph
+    if use_graph:
+        from two_tower_models_b200.graph import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, dev_ring[0], post_backward=sync)
+
+        def step(b):  # D2D copy of the batch into the captured inputs + one graph launch
+            return gstep(b)
+    else:
+        def step(b):
+            model._packed.invalidate()
+            model.zero_grad(set_to_none=True)
+            loss = model.train_forward(*[b[k] for k in ORDER])
+            loss.backward()
+            if sync is not None:
+                sync(model)
+            return loss.detach()
+
+    def eager_step(b):
+        model._packed.invalidate()
         model.zero_grad(set_to_none=True)
         loss = model.train_forward(*[b[k] for k in ORDER])
         loss.backward()
-        return loss
+        if sync is not None:
+            sync(model)
+        return loss.detach()
 
     def barrier():
         if world > 1:
@@ -222,8 +245,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.TIMER = ops.KernelTimer()
     l0 = ops.launch_count()
+    eager_step(dev_ring[0])
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0  # the captured graph replays exactly these launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -232,9 +257,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - l0
-    spans = ops.TIMER.totals_ms()
-    ops.TIMER = None
+    launches = launches_per_step * K
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -242,35 +265,44 @@ def main():
     value = B * world / (ms_step * 1e-3)
     loss_val = float(loss.item())
 
+    # per-kernel device time of the scoring kernels: CUDA-event spans on the launching stream, eager launches
+    # of the very same kernels on the same inputs (events cannot be recorded inside a replayed graph)
+    ops.TIMER = ops.KernelTimer()
+    for i in range(max(3, min(K, 10))):
+        eager_step(dev_ring[(W + i) % RING])
+    spans = ops.TIMER.totals_ms()
+    ops.TIMER = None
+
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
-    copy_stream = torch.cuda.Stream(device=dev)
-    slots = [{k: torch.empty_like(v, device=dev) for k, v in host_ring[0].items()} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(K + W, dtype=torch.float32).pin_memory()
+    if True:  # double-buffered H2D on a copy stream; the step (graph replay) starts with a D2D into its inputs
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = [{k: torch.empty_like(v, device=dev) for k, v in host_ring[0].items()} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
 
-    def upload(i):
-        s = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[s])
-            for k in ORDER:
-                slots[s][k].copy_(host_ring[i % RING][k], non_blocking=True)
-            ready[s].record(copy_stream)
-
-    def e2e_steps(n0, n):
-        cur = torch.cuda.current_stream()
-        upload(n0)
-        for i in range(n0, n0 + n):
-            if i + 1 < n0 + n:
-                upload(i + 1)  # prefetch the next batch while this one computes
+        def upload(i):
             s = i % 2
-            cur.wait_event(ready[s])
-            l = step(slots[s])
-            freed[s].record(cur)
-            loss_host[i].copy_(l.detach(), non_blocking=True)  # D2H read of the step's result
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                for k in ORDER:
+                    slots[s][k].copy_(host_ring[i % RING][k], non_blocking=True)
+                ready[s].record(copy_stream)
 
-    for s in range(2):
-        freed[s].record(torch.cuda.current_stream())
+        def e2e_steps(n0, n):
+            cur = torch.cuda.current_stream()
+            upload(n0)
+            for i in range(n0, n0 + n):
+                if i + 1 < n0 + n:
+                    upload(i + 1)  # prefetch the next batch while this one computes
+                s = i % 2
+                cur.wait_event(ready[s])
+                l = step(slots[s])
+                freed[s].record(cur)
+                loss_host[i].copy_(l.detach(), non_blocking=True)  # D2H read of the step's result
+
+        for s in range(2):
+            freed[s].record(torch.cuda.current_stream())
     e2e_steps(0, W)
     barrier()
     t0 = time.perf_counter()
@@ -337,7 +369,7 @@ def main():
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms},
-        "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "gpu_launches": int(launches), "launches_per_step": launches_per_step, "cuda_graph": use_graph,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "loss": loss_val,
     }
     print(json.dumps(out), flush=True)

@@ -64,12 +64,14 @@ int tt_colsum(const void* src_bf16, const float* src_f32, int64_t rows, int64_t 
  * A: bf16 [M,K] pitch lda, or (a_mn_major) stored as [K,M] pitch lda.  B: bf16 [N,K] or (b_mn_major) [K,N].
  * Outputs: c_f32 (pitch ldc_f32) and/or c_bf16 (pitch ldc_bf16).  accumulate != 0: split-K with fp32
  * atomicAdd into c_f32 (no bias/relu/mask/bf16 output; caller initialises c_f32); split_k 0 = auto.
+ * colsum_f32 (may be NULL): [N] fp32, += sum over rows of the final C values taken from the fp32
+ * accumulators (bias gradients; caller initialises).
  * Replaces nn.Linear forward/backward (reference :76-80, :90-93, :101-110) and the MHA in/out
  * projections (src/user_history_encoder.py:60-67). */
 int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                  int64_t M, int64_t N, int64_t K, const float* bias, int32_t relu, const void* relu_mask_bf16,
                  int64_t ld_mask, float alpha, float* c_f32, int64_t ldc_f32, void* c_bf16, int64_t ldc_bf16,
-                 int32_t accumulate, int32_t split_k, void* stream);
+                 int32_t accumulate, int32_t split_k, float* colsum_f32, void* stream);
 
 /* ---- in-batch sampled-softmax loss ---------------------------------------------------------- */
 
@@ -90,6 +92,12 @@ int tt_inbatch_ce_bwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64
                       int64_t target_offset, const float* lse, const float* g, float* dU_f32, int64_t lddu,
                       void* dU_bf16, int64_t lddu16, float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16,
                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Value-weighted mean of the per-row loss with the identity debias hook (reference
+ * src/two_tower_base_retrieval.py:322-343): nuv_i = sum_t labels[i,t] * weights[t]; w_i = max(nuv_i, 1e-6) /
+ * max_i(max(nuv_i, 1e-6)); *loss = sum_i ce[i] w_i / B; g[i] = d loss / d ce[i] = w_i / B.  One launch. */
+int tt_weighted_loss(const float* ce, const float* labels, int64_t ld_labels, const float* weights, int64_t B, int64_t T,
+                     float* loss, float* g, void* stream);
 
 /* ---- brute-force MIPS ------------------------------------------------------------------------ */
 

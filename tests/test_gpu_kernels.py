@@ -88,6 +88,24 @@ def test_gemm_epilogue_bias_relu_mask_alpha():
     assert torch.equal(out.cpu(), ref), _report("mask+alpha", out, ref)
 
 
+def test_gemm_fused_column_sums():
+    """colsum += sum over rows of the final (masked) outputs, taken from the fp32 accumulators."""
+    from two_tower_models_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    M, N, K = 777, 200, 96
+    A, B = _grid((M, K), g), _grid((N, K), g)
+    mask = _grid((M, N), g, -1, 2)
+    dev = _dev()
+    A16, B16, mask16 = ops.cast_rows_bf16(A.to(dev)), ops.cast_rows_bf16(B.to(dev)), ops.cast_rows_bf16(mask.to(dev))
+    out16 = torch.empty((M, ops._r8(N)), dtype=torch.bfloat16, device=dev)
+    cs = torch.zeros(N, device=dev)
+    ops.gemm(A16, B16, M, N, K, relu_mask=mask16, out16=out16, colsum=cs)
+    ref = (A @ B.t()) * (mask > 0)
+    assert torch.equal(cs.cpu(), ref.sum(0)), _report("colsum", cs, ref.sum(0))
+    assert torch.equal(out16[:, :N].float().cpu(), bf16_round(ref))
+
+
 def test_gemm_split_k_accumulate():
     from two_tower_models_b200 import ops
 

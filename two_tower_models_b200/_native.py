@@ -28,10 +28,11 @@ SIGNATURES = {
     "tt_gather_rows_f32": (I32, [P, I64, I64, P, I64, P, I64, P, P]),
     "tt_scatter_add_rows": (I32, [P, P, I64, P, I64, I64, P, I64, P]),
     "tt_colsum": (I32, [P, P, I64, I64, I64, P, P]),
-    "tt_gemm_bf16": (I32, [P, I64, I32, P, I64, I32, I64, I64, I64, P, I32, P, I64, F32, P, I64, P, I64, I32, I32, P]),
+    "tt_gemm_bf16": (I32, [P, I64, I32, P, I64, I32, I64, I64, I64, P, I32, P, I64, F32, P, I64, P, I64, I32, I32, P, P]),
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, I64, P]),
+    "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_history_gather_pool": (I32, [P, I64, I64, P, I64, I64, P, P, I64, P, I64, P, P]),

@@ -108,7 +108,7 @@ int tt_colsum(const void* src16, const float* src32, int64_t rows, int64_t cols,
 int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                  int64_t M, int64_t N, int64_t K, const float* bias, int32_t relu, const void* relu_mask, int64_t ld_mask,
                  float alpha, float* c_f32, int64_t ldc_f32, void* c_bf16, int64_t ldc_bf16, int32_t accumulate,
-                 int32_t split_k, void* stream) {
+                 int32_t split_k, float* colsum_f32, void* stream) {
   GemmDesc d;
   d.A = A; d.lda = lda; d.a_mn_major = a_mn_major;
   d.B = B; d.ldb = ldb; d.b_mn_major = b_mn_major;
@@ -116,7 +116,7 @@ int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, 
   d.bias = bias; d.relu = relu; d.relu_mask = relu_mask; d.ld_mask = ld_mask;
   d.alpha = alpha;
   d.c32 = c_f32; d.ldc32 = ldc_f32; d.c16 = c_bf16; d.ldc16 = ldc_bf16;
-  d.accumulate = accumulate; d.split_k = split_k;
+  d.accumulate = accumulate; d.split_k = split_k; d.colsum = colsum_f32;
   return gemm_bf16(d, S(stream));
 }
 
@@ -133,6 +133,11 @@ int tt_inbatch_ce_bwd(const void* U, int64_t ldu, const void* V, int64_t ldv, in
                       void* stream) {
   return inbatch_ce_bwd(U, ldu, V, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16, lddv16,
                         ws, (size_t)ws_bytes, S(stream));
+}
+
+int tt_weighted_loss(const float* ce, const float* labels, int64_t ldl, const float* weights, int64_t B, int64_t T,
+                     float* loss, float* g, void* stream) {
+  return weighted_loss(ce, labels, ldl, weights, B, T, loss, g, S(stream));
 }
 
 int64_t tt_mips_workspace_bytes(int64_t nq, int64_t nc, int64_t d, int64_t k) {

@@ -209,4 +209,63 @@ int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, l
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// value-weighted mean of the per-row cross entropy (reference src/two_tower_base_retrieval.py:322-343
+// with the identity debias hook):  nuv_i = sum_t labels[i,t] w_t;  w_i = max(nuv_i, 1e-6) / max_i(.);
+// loss = sum_i ce_i w_i / B;  g_i = d loss / d ce_i = w_i / B.   One CTA, two passes over B rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+weighted_loss_kernel(const float* __restrict__ ce, const float* __restrict__ labels, long long ldl,
+                     const float* __restrict__ uvw, int B, int T, float inv_rows, float* __restrict__ loss,
+                     float* __restrict__ g) {
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = 0.f;
+  for (int i = tid; i < B; i += blockDim.x) {
+    float nuv = 0.f;
+    for (int t = 0; t < T; ++t) nuv = fmaf(labels[(long long)i * ldl + t], uvw[t], nuv);
+    nuv = fmaxf(nuv, 0.000001f);
+    g[i] = nuv;  // parked until the maximum is known
+    mx = fmaxf(mx, nuv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float m = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) bcast = m;
+  }
+  __syncthreads();
+  const float inv_max = 1.f / bcast;
+  float acc = 0.f;
+  for (int i = tid; i < B; i += blockDim.x) {
+    const float w = g[i] * inv_max;
+    acc = fmaf(ce[i], w, acc);
+    g[i] = w * inv_rows;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float a = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) *loss = a * inv_rows;
+  }
+}
+int weighted_loss(const float* ce, const float* labels, long long ldl, const float* uvw, long long B, long long T,
+                  float* loss, float* g, cudaStream_t stream) {
+  TT_CHECK(B > 0 && T > 0 && ldl >= T, "weighted_loss: bad shape");
+  weighted_loss_kernel<<<1, 1024, 0, stream>>>(ce, labels, ldl, uvw, (int)B, (int)T, 1.f / (float)B, loss, g);
+  TT_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace tt

@@ -35,6 +35,8 @@ struct GemmArgs {
   float alpha;
   int vec32, vec16, vecmask;
   int mn_lbo, mn_sbo, mn_kadv;  // MN-major descriptor strides (bytes)
+  float* colsum;                 // optional [N] fp32, += column sums of the final C values
+  unsigned long long* trace;     // bring-up: per-CTA %globaltimer stamps (TT_GEMM_TRACE), normally null
 };
 
 template <int BN>
@@ -61,6 +63,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#define TT_STAMP(slot)                                                             \
+  do {                                                                             \
+    if (g.trace != nullptr && lane == 0) {                                         \
+      unsigned long long t_;                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+      g.trace[(size_t)blockIdx.x * 8 + (slot)] = t_;                               \
+    }                                                                              \
+  } while (0)
+  if (warp == 3) TT_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma);
@@ -82,6 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (warp == 3) TT_STAMP(1);
 
   const int total_work = g.m_tiles * g.n_tiles * g.splits;
 
@@ -135,6 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == kb0 && w == (int)blockIdx.x) TT_STAMP(2);
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
@@ -161,6 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (warp == 4 && w == (int)blockIdx.x) TT_STAMP(3);
       const long long row = (long long)m_tile * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
 #pragma unroll 1
@@ -169,36 +183,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         if (n0 >= g.N) break;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
-        tmem_wait_ld();
+        // operands of the epilogue are fetched while the TMEM load is in flight
         const bool full = (n0 + 32 <= g.N);
+        const float bias_l = (g.bias != nullptr && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
+        uint4 mv[4];
+        const bool vmask = g.mask != nullptr && row_ok && full && g.vecmask;
+        if (vmask) {
+          const bf16* mp = g.mask + row * g.ld_mask + n0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mv[j] = *reinterpret_cast<const uint4*>(mp + j * 8);
+        }
+        tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = v[j] * g.alpha;
-          if (g.bias != nullptr && (full || n0 + j < g.N)) x += __ldg(g.bias + n0 + j);
+          float x = fmaf(v[j], g.alpha, __shfl_sync(0xffffffffu, bias_l, j));
           if (g.relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
-        if (row_ok) {
-          if (g.mask != nullptr) {
-            const bf16* mp = g.mask + row * g.ld_mask + n0;
-            if (full && g.vecmask) {
+        if (g.mask != nullptr && row_ok) {
+          if (vmask) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 mv = *reinterpret_cast<const uint4*>(mp + j * 8);
-                const bf16* mb = reinterpret_cast<const bf16*>(&mv);
+            for (int j = 0; j < 4; ++j) {
+              const bf16* mb = reinterpret_cast<const bf16*>(&mv[j]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (!(__bfloat162float(mb[e]) > 0.f)) v[j * 8 + e] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < g.N && !(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
+              for (int e = 0; e < 8; ++e)
+                if (!(__bfloat162float(mb[e]) > 0.f)) v[j * 8 + e] = 0.f;
             }
+          } else {
+            const bf16* mp = g.mask + row * g.ld_mask + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N && !(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
           }
+        }
+        if (row_ok) {
           if (g.c32 != nullptr) {
             float* cp = g.c32 + row * g.ldc32 + n0;
-            if (g.atomic32) {
+            if (g.atomic32 && full && g.vec32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)  // 16-byte vector reductions: 4x fewer L2 atomic transactions
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j * 4), "f"(v[4 * j]),
+                             "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                             : "memory");
+            } else if (g.atomic32) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (n0 + j < g.N) atomicAdd(cp + j, v[j]);
@@ -231,10 +258,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
             }
           }
         }
+        if (g.colsum != nullptr) {
+          // fp32 column sums of the tile (bias gradients): butterfly transpose-reduce over the 32 rows held
+          // by this warp, after which lane l owns column n0 + l; one atomic per column per warp.
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = up ? v[i] : v[i + off];
+              const float keep = up ? v[i + off] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (n0 + lane < g.N) atomicAdd(g.colsum + n0 + lane, v[0]);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (warp == 4 && w == (int)blockIdx.x) TT_STAMP(4);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -245,6 +292,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (warp == 3) TT_STAMP(5);
+#undef TT_STAMP
 }
 
 template <int BN>
@@ -268,15 +317,23 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   TT_CHECK(d.A && d.B, "gemm: null operand");
   TT_CHECK((d.lda % 8) == 0 && (d.ldb % 8) == 0, "gemm: operand pitches must be multiples of 8 elements (lda=%lld ldb=%lld)", d.lda, d.ldb);
   TT_CHECK(((uintptr_t)d.A % 16) == 0 && ((uintptr_t)d.B % 16) == 0, "gemm: operands must be 16-byte aligned");
-  TT_CHECK(d.c32 || d.c16, "gemm: no output");
+  TT_CHECK(d.c32 || d.c16 || d.colsum, "gemm: no output");
 
   int BN = 64;
-  {  // largest tile with the least padded columns
-    long long best = -1;
+  {  // fewest padded columns first; then the widest tile that still gives ~one CTA per SM, else the narrowest
+    const long long m_tiles = (d.M + BM - 1) / BM;
+    long long best_pad = -1;
     const int cand[3] = {256, 128, 64};
     for (int i = 0; i < 3; ++i) {
-      long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
-      if (best < 0 || padded < best) { best = padded; BN = cand[i]; }
+      const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
+      if (best_pad < 0 || padded < best_pad) best_pad = padded;
+    }
+    bool found = false;
+    for (int i = 0; i < 3 && !found; ++i) {
+      const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
+      if (padded != best_pad) continue;
+      BN = cand[i];  // ends at the narrowest candidate with minimal padding
+      if (m_tiles * (padded / cand[i]) * 4 >= 3ll * num_sms()) found = true;
     }
   }
   GemmArgs g;
@@ -291,6 +348,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
     if (splits <= 0) {
       const int tiles = g.m_tiles * g.n_tiles;
       splits = tiles >= num_sms() ? 1 : (num_sms() + tiles - 1) / tiles;
+      const int max_useful = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;  // >= 8 k-blocks per CTA: fewer atomics
+      if (splits > max_useful) splits = max_useful;
     }
     if (splits > g.kb_total) splits = g.kb_total;
   }
@@ -301,6 +360,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   g.c32 = d.c32; g.ldc32 = d.ldc32; g.atomic32 = d.accumulate ? 1 : 0;
   g.c16 = (bf16*)d.c16; g.ldc16 = d.ldc16;
   g.alpha = d.alpha;
+  g.colsum = d.colsum;
   g.vec32 = d.c32 && (d.ldc32 % 4 == 0) && ((uintptr_t)d.c32 % 16 == 0);
   g.vec16 = d.c16 && (d.ldc16 % 8 == 0) && ((uintptr_t)d.c16 % 16 == 0);
   g.vecmask = d.relu_mask && (d.ld_mask % 8 == 0) && ((uintptr_t)d.relu_mask % 16 == 0);
@@ -308,7 +368,9 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   if (const char* dbg = getenv("TT_DBG_MN")) {  // bring-up knob: "lbo,sbo,kadv"
     sscanf(dbg, "%d,%d,%d", &g.mn_lbo, &g.mn_sbo, &g.mn_kadv);
   }
-  TT_CHECK(!(d.accumulate && (d.bias || d.relu || d.relu_mask || d.c16)),
+  g.trace = nullptr;
+  if (const char* tr = getenv("TT_GEMM_TRACE")) g.trace = (unsigned long long*)strtoull(tr, nullptr, 0);
+  TT_CHECK(!(d.accumulate && (d.bias || d.relu || d.relu_mask || d.c16 || d.colsum)),
            "gemm: split-K accumulation only supports a plain fp32 output");
 
   CUtensorMap ta, tb;

@@ -24,6 +24,7 @@ struct GemmDesc {
   int accumulate = 0;  // fp32 atomicAdd into c32 (split-K); c32 must be initialised by the caller
   int split_k = 0;     // 0 = auto
   float alpha = 1.f;
+  float* colsum = nullptr;  // optional [N] fp32: += column sums of the final C (caller initialises)
 };
 int gemm_bf16(const GemmDesc& d, cudaStream_t stream);
 
@@ -67,5 +68,8 @@ int history_gather_pool(const float* table, long long table_rows, long long D, c
 int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, long long lddmean,
                          const long long* ids, long long B, long long H, long long D, float* table_grad,
                          long long table_rows, cudaStream_t stream);
+
+int weighted_loss(const float* ce, const float* labels, long long ldl, const float* uvw, long long B, long long T,
+                  float* loss, float* g, cudaStream_t stream);
 
 }  // namespace tt

@@ -120,7 +120,7 @@ def cast_rows_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None, col_of
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False, b_mn=False,
          bias: Optional[torch.Tensor] = None, relu=False, relu_mask: Optional[torch.Tensor] = None,
          alpha: float = 1.0, out32: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None,
-         accumulate=False, split_k=0) -> None:
+         accumulate=False, split_k=0, colsum: Optional[torch.Tensor] = None) -> None:
     """C = alpha*A*B^T (+bias)(relu)(mask); A,B bf16 2-D views (last stride 1); see tt_gemm_bf16."""
     L = _native.lib()
     _native.check(
@@ -128,7 +128,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False
                        _ptr(bias), int(relu), _ptr(relu_mask), relu_mask.stride(0) if relu_mask is not None else 0,
                        alpha, _ptr(out32), out32.stride(0) if out32 is not None else 0,
                        _ptr(out16), out16.stride(0) if out16 is not None else 0,
-                       int(accumulate), split_k, _stream()),
+                       int(accumulate), split_k, _ptr(colsum), _stream()),
         "gemm_bf16",
     )
 
@@ -209,6 +209,12 @@ class PackedWeights:
 
     def __init__(self):
         self._cache = {}
+        self._force = False
+
+    def invalidate(self):
+        """Re-pack every weight on its next use (the buffers are kept and overwritten in place)."""
+        for k, (ver, out) in list(self._cache.items()):
+            self._cache[k] = (None, out)
 
     def get(self, key, param: torch.Tensor, segments=None) -> torch.Tensor:
         """segments: list of (src_col0, cols, dst_col0) placing column blocks at 8-aligned offsets."""
@@ -220,7 +226,11 @@ class PackedWeights:
         with torch.no_grad():
             src = _f32c(param.detach())
             if segments is None:
-                out = cast_rows_bf16(src)
+                if hit is not None and hit[1].shape == (rows, _r8(cols)) and hit[1].device == param.device:
+                    out = hit[1]
+                    cast_rows_bf16(src, out=out, cols=cols)
+                else:
+                    out = cast_rows_bf16(src)
             else:
                 width = max(d0 + _r8(c) for (_, c, d0) in segments)
                 out = hit[1] if (hit is not None and hit[1].shape == (rows, width)) else torch.zeros(
@@ -245,19 +255,18 @@ def _mlp_forward(feats16, F, w0_16, b0, w1_16, b1, D, out16=None, out16_col=0, o
     return H16
 
 
-def _mlp_backward(dFe16, D, feats16, F, H16, w0_16, w1_16, need_dfeats=False):
-    """Gradients of the feature MLP given dFe (bf16 view [rows, >=D])."""
+def _mlp_backward(dFe16, db1, D, feats16, F, H16, w0_16, w1_16, need_dfeats=False):
+    """Gradients of the feature MLP given dFe (bf16 view [rows, >=D]) and its fp32 column sums db1."""
     rows = feats16.shape[0]
     hid = H16.shape[1]
     dev = feats16.device
     dW1 = torch.zeros((D, hid), dtype=torch.float32, device=dev)
     gemm(dFe16, H16, D, hid, rows, a_mn=True, b_mn=True, out32=dW1, accumulate=True)
-    db1 = colsum(dFe16, D)
     dH16 = torch.empty((rows, hid), dtype=_BF16, device=dev)
-    gemm(dFe16, w1_16, rows, hid, D, b_mn=True, relu_mask=H16, out16=dH16)
+    db0 = torch.zeros(hid, dtype=torch.float32, device=dev)
+    gemm(dFe16, w1_16, rows, hid, D, b_mn=True, relu_mask=H16, out16=dH16, colsum=db0)  # db0 from the fp32 accumulators
     dW0 = torch.zeros((hid, F), dtype=torch.float32, device=dev)
     gemm(dH16, feats16, hid, F, rows, a_mn=True, b_mn=True, out32=dW0, accumulate=True)
-    db0 = colsum(dH16, hid)
     dfeats = None
     if need_dfeats:
         dfeats = torch.empty((rows, F), dtype=torch.float32, device=dev)
@@ -317,9 +326,10 @@ class TowerFunction(torch.autograd.Function):
         # tower Linear
         dWt_p = torch.zeros((DI, KT), dtype=torch.float32, device=dev)
         gemm(demb16, X16, DI, KT, B, a_mn=True, b_mn=True, out32=dWt_p, accumulate=True)
-        dbt = colsum(demb16, DI)
+        dbt = colsum(_f32c(demb), DI)  # fp32 source: item-side bias gradients are analytically zero sums
         dX16 = torch.empty((B, KT), dtype=_BF16, device=dev)
-        gemm(demb16, wt_16, B, KT, DI, b_mn=True, out16=dX16)
+        dXsum = torch.zeros(KT, dtype=torch.float32, device=dev)
+        gemm(demb16, wt_16, B, KT, DI, b_mn=True, out16=dX16, colsum=dXsum)
         if D8 == D and _r8(E) == E:
             dWt = dWt_p
         else:
@@ -328,7 +338,8 @@ class TowerFunction(torch.autograd.Function):
         # id embedding (dense gradient, duplicates accumulate)
         dtable = scatter_add_rows(dX16, ids, D, table_rows, col_offset=0)
         # feature MLP
-        dW0, db0, dW1, db1, dfeats = _mlp_backward(dX16[:, D8:], D, feats16, F, H16, w0_16, w1_16, ctx.need_dfeats)
+        dW0, db0, dW1, db1, dfeats = _mlp_backward(dX16[:, D8:], dXsum[D8:D8 + D], D, feats16, F, H16, w0_16, w1_16,
+                                                   ctx.need_dfeats)
         dextra = dX16[:, 2 * D8:2 * D8 + E].float() if ctx.has_extra else None
         return None, dfeats, dextra, dtable, dW0, db0, dW1, db1, dWt, dbt, None, None
 
@@ -377,8 +388,10 @@ class FeatureMLPFunction(torch.autograd.Function):
     def backward(ctx, dout):
         feats16, H16, w0_16, w1_16 = ctx.saved_tensors
         F, D = ctx.dims
-        d16 = cast_rows_bf16(_f32c(dout))
-        dW0, db0, dW1, db1, dfeats = _mlp_backward(d16, D, feats16, F, H16, w0_16, w1_16, ctx.need_dfeats)
+        dout = _f32c(dout)
+        d16 = cast_rows_bf16(dout)
+        dW0, db0, dW1, db1, dfeats = _mlp_backward(d16, colsum(dout, D), D, feats16, F, H16, w0_16, w1_16,
+                                                   ctx.need_dfeats)
         return dfeats, dW0, db0, dW1, db1, None, None
 
 
@@ -412,7 +425,7 @@ class LinearFunction(torch.autograd.Function):
             dy16 = cast_rows_bf16(_f32c(dy))
         dW = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
         gemm(dy16, x16, N, K, B, a_mn=True, b_mn=True, out32=dW, accumulate=True)
-        db = colsum(dy16, N) if ctx.has_bias else None
+        db = colsum(_f32c(dy), N) if ctx.has_bias else None
         dx = None
         if ctx.need_dx:
             dx = torch.empty((B, K), dtype=torch.float32, device=dy.device)
@@ -494,6 +507,30 @@ class InBatchCEFunction(torch.autograd.Function):
 
 def inbatch_cross_entropy(U: torch.Tensor, V: torch.Tensor, target_offset: int = 0) -> torch.Tensor:
     return InBatchCEFunction.apply(U, V, target_offset)
+
+
+class WeightedLossFunction(torch.autograd.Function):
+    """loss = mean(ce * clamp(labels @ w, 1e-6) / max(.)) in one launch (reference :322-343, identity hook)."""
+
+    @staticmethod
+    def forward(ctx, ce, labels, weights):
+        _need_cuda(ce, labels, weights)
+        ce, labels, weights = _f32c(ce), _f32c(labels), _f32c(weights)
+        B, T = labels.shape
+        loss = torch.empty((), dtype=torch.float32, device=ce.device)
+        g = torch.empty(B, dtype=torch.float32, device=ce.device)
+        _native.check(
+            _native.lib().tt_weighted_loss(ce.data_ptr(), labels.data_ptr(), labels.stride(0), weights.data_ptr(), B, T,
+                                           loss.data_ptr(), g.data_ptr(), _stream()),
+            "weighted_loss",
+        )
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (g,) = ctx.saved_tensors
+        return g * dloss, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -627,6 +664,7 @@ class HistoryEncoderFunction(torch.autograd.Function):
         D8 = _r8(D)
         ds = _f32c(dsummary)
         dy16 = cast_rows_bf16(ds, cols=D)  # gradient of the last layer's row-0 output, [B, D8]
+        dy_sum = colsum(ds[:, :D], D)      # its fp32 column sums (= last out-projection bias gradient)
         dmean = ds[:, D:]
         grads = [None] * (4 * L)
         for l in range(L - 1, -1, -1):
@@ -636,7 +674,7 @@ class HistoryEncoderFunction(torch.autograd.Function):
             rows = B * q_rows
             d_out_w = torch.zeros((D, D), dtype=torch.float32, device=dev)
             gemm(dy16, o16, D, D, rows, a_mn=True, b_mn=True, out32=d_out_w, accumulate=True)
-            d_out_b = colsum(dy16, D)
+            d_out_b = dy_sum
             do16 = torch.empty((rows, D8), dtype=_BF16, device=dev)
             gemm(dy16, out_w16, rows, D, D, b_mn=True, out16=do16)
             dqkv16 = attn_backward(qkv16, do16, B, H, D, heads, q_rows)
@@ -644,7 +682,8 @@ class HistoryEncoderFunction(torch.autograd.Function):
             gemm(dqkv16, x16, 3 * D, D, B * H, a_mn=True, b_mn=True, out32=d_in_w, accumulate=True)
             d_in_b = colsum(dqkv16, 3 * D)
             dx16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
-            gemm(dqkv16, in_w16, B * H, D, 3 * D, b_mn=True, out16=dx16)
+            dy_sum = torch.zeros(D, dtype=torch.float32, device=dev)  # bias gradient of the layer below
+            gemm(dqkv16, in_w16, B * H, D, 3 * D, b_mn=True, out16=dx16, colsum=dy_sum)
             grads[4 * l: 4 * l + 4] = [d_in_w, d_in_b, d_out_w, d_out_b]
             dy16 = dx16
         dtable = torch.zeros((table_rows, D), dtype=torch.float32, device=dev)

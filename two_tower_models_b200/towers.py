@@ -10,7 +10,11 @@ from typing import List, Optional, Tuple
 import torch
 import torch.nn as nn
 
+import os
+
 from . import ops
+
+_OVERLAP_TOWERS = os.environ.get("TT_B200_OVERLAP_TOWERS", "1") == "1"
 
 
 class TwoTowerBaseRetrieval(nn.Module):
@@ -49,6 +53,14 @@ class TwoTowerBaseRetrieval(nn.Module):
 
         self._packed = ops.PackedWeights()  # bf16 operand copies of the weights
         self._dp = None  # optional data-parallel context, see distributed.enable_data_parallel
+        self._streams = {}  # device -> side stream for the item tower
+
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        st = self._streams.get(device)
+        if st is None:
+            st = torch.cuda.Stream(device=device)
+            self._streams[device] = st
+        return st
 
     # ------------------------------------------------------------------ user tower
     def get_user_embedding(self, user_id: torch.Tensor, user_features: torch.Tensor) -> torch.Tensor:
@@ -141,6 +153,14 @@ class TwoTowerBaseRetrieval(nn.Module):
         if self._dp is not None:
             return self._dp.compute_training_loss(self, user_embedding, item_embeddings, position, labels)
         loss = ops.inbatch_cross_entropy(user_embedding, item_embeddings)  # [B]
+        if (
+            type(self).debias_net_user_value is TwoTowerBaseRetrieval.debias_net_user_value
+            and labels.dim() == 2
+            and labels.shape[1] == self.user_value_weights.shape[0]
+            and not labels.requires_grad
+        ):
+            # identity hook: weights, batch max and the weighted mean in one launch
+            return ops.WeightedLossFunction.apply(loss, labels, self.user_value_weights)
         net_user_value = torch.sum(labels * self.user_value_weights, dim=-1)  # [B]
         net_user_value, additional_loss = self.debias_net_user_value(
             net_user_value=net_user_value, position=position, user_embedding=user_embedding
@@ -160,9 +180,27 @@ class TwoTowerBaseRetrieval(nn.Module):
         position: torch.Tensor,  # [B]
         labels: torch.Tensor,  # [B, T]
     ) -> torch.Tensor:
-        """Training loss, a 0-dim fp32 tensor with grad_fn (reference :349-394)."""
-        user_embedding = self.compute_user_embedding(user_id, user_features, user_history)
-        item_embeddings = self.compute_item_embeddings(item_id, item_features)
+        """Training loss, a 0-dim fp32 tensor with grad_fn (reference :349-394).
+
+        The two towers are independent until the loss, so the item tower is enqueued on a second CUDA
+        stream (forked from / joined to the caller's stream; autograd replays the same split in backward):
+        each tower is a chain of small launch-latency-bound kernels that fills half of the SMs at most.
+        """
+        if _OVERLAP_TOWERS and item_id.is_cuda:
+            cur = torch.cuda.current_stream(item_id.device)
+            side = self._side_stream(item_id.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                item_embeddings = self.compute_item_embeddings(item_id, item_features)
+            user_embedding = self.compute_user_embedding(user_id, user_features, user_history)
+            cur.wait_stream(side)
+            item_embeddings.record_stream(cur)
+            shadow = getattr(item_embeddings, "_tt_bf16", None)
+            if shadow is not None:
+                shadow.record_stream(cur)
+        else:
+            user_embedding = self.compute_user_embedding(user_id, user_features, user_history)
+            item_embeddings = self.compute_item_embeddings(item_id, item_features)
         return self.compute_training_loss(
             user_embedding=user_embedding, item_embeddings=item_embeddings, position=position, labels=labels
         )
