@@ -1,0 +1,39 @@
+"""Bring-up: clock64 timeline of CTA 0 of the CE backward kernel (TT_CE_TRACE)."""
+import os, sys
+import torch
+sys.path.insert(0, ".")
+from two_tower_models_b200 import ops
+dev = torch.device("cuda:0")
+B = N = 8192; d = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+U = (torch.randn(B, d, device=dev) * 0.4).to(torch.bfloat16); V = (torch.randn(N, d, device=dev) * 0.4).to(torch.bfloat16)
+ce, lse = ops.inbatch_ce_forward_raw(U, V, B, N, d, 0)
+g = torch.full((B,), 1.0 / B, device=dev)
+for _ in range(2): ops.inbatch_ce_backward_raw(U, V, B, N, d, 0, lse, g)
+torch.cuda.synchronize()
+tr = torch.zeros(4 * 64 * 2, dtype=torch.int64, device=dev)
+os.environ["TT_CE_TRACE"] = str(tr.data_ptr())
+lib = __import__("two_tower_models_b200._native", fromlist=["lib"]).lib()
+if len(sys.argv) > 2 and sys.argv[2] == "fwd":
+    ops.inbatch_ce_forward_raw(U, V, B, N, d, 0)
+    torch.cuda.synchronize()
+    t = tr.cpu().view(4, 64, 2)
+    t0 = int(t[t > 0].min())
+    print("tile | MMA loop top, Y landed, S issued | epilogue g0 start->end | epilogue g1 start->end")
+    for i in range(28):
+        g = lambda r, w: int(t[r, i, w]) - t0
+        print(f"{i:3d} | {g(0,0):7d} {g(1,0):7d} {g(0,1):7d} | {g(2,0):7d} {g(2,1):7d} | {g(3,0):7d} {g(3,1):7d}")
+    sys.exit(0)
+# only the dU pass (dV outputs NULL) so that the trace is not overwritten by the second pass
+dU = torch.empty(B, d, device=dev); ws = ops._ce_workspace(B, N, d, dev)
+rc = lib.tt_inbatch_ce_bwd(U.data_ptr(), U.stride(0), V.data_ptr(), V.stride(0), B, N, d, 0, lse.data_ptr(), g.data_ptr(),
+                           dU.data_ptr(), dU.stride(0), None, 0, None, 0, None, 0, ws.data_ptr(), ws.numel(),
+                           torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+t = tr.cpu().view(4, 64, 2)
+t0 = int(t[t > 0].min())
+print("tile | S-MMA wait->issue | PV-MMA wait->issue | epilogue g0 start->end | epilogue g1 start->end   (cycles since start)")
+for i in range(28):
+    def f(r):
+        a, b = int(t[r, i, 0]), int(t[r, i, 1])
+        return f"{a - t0 if a else -1:7d} {b - t0 if b else -1:7d}"
+    print(f"{i:3d} | {f(0)} | {f(1)} | {f(2)} | {f(3)}")

@@ -18,6 +18,8 @@
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
 // warps 4-7 / 8-11 two epilogue warpgroups that alternate score tiles (TMEM buffer e <-> group e).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -73,11 +75,13 @@ struct CeFwdArgs {
   float* part_m;
   float* part_s;
   float* diag;
+  long long* trace;  // bring-up (TT_CE_TRACE)
 };
 
 template <int DP>
 struct CeFwdCfg {
   static constexpr int BN = 128;
+  static constexpr int NS = 4;  // score-tile buffers in TMEM (4 x 128 columns)
   static constexpr int KBOX = DP / 64;
   static constexpr int X_BYTES = 128 * DP * 2;
   static constexpr int Y_BYTES = BN * DP * 2;
@@ -85,11 +89,15 @@ struct CeFwdCfg {
   static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + 1024 + 256;
 };
 
+// Both epilogue groups work on EVERY score tile, each on one half of its columns (group e: columns
+// [64 e, 64 e + 64)), so all 8 epilogue warps are busy on the tile that is ready while the UMMA warp runs up
+// to NS - 1 tiles ahead.  A row's running (max, sum-exp) is therefore split over two threads; the combine
+// kernel merges the (slot, group) partials.
 template <int DP>
 __global__ void __launch_bounds__(384, 1)
 ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeFwdArgs a) {
   using Cfg = CeFwdCfg<DP>;
-  constexpr int BN = Cfg::BN;
+  constexpr int BN = Cfg::BN, NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sx = smem;
@@ -97,11 +105,11 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   uint64_t* bars = reinterpret_cast<uint64_t*>(sy + Cfg::STAGES * Cfg::Y_BYTES);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 1;
-  uint64_t* y_full = bars + 2;
+  uint64_t* s_full = bars + 2;
+  uint64_t* s_empty = s_full + NS;
+  uint64_t* y_full = s_empty + NS;
   uint64_t* y_empty = y_full + Cfg::STAGES;
-  uint64_t* s_full = y_empty + Cfg::STAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -115,13 +123,13 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  if (warp == 2) tmem_alloc(tmem_holder, NS * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,37 +157,40 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       SegIter it(a.T, a.total, a.CT);
       int r, j0, j1, stage = 0;
       uint32_t phase = 0, xs = 0, t = 0;
-      const uint32_t sxa = smem_u32(sx);
+      const uint64_t dx0 = make_smem_desc_sw128(smem_u32(sx), 0, 1024);
+      const uint64_t dy0 = make_smem_desc_sw128(smem_u32(sy), 0, 1024);
       while (it.next(r, j0, j1)) {
         mbar_wait(x_full, xs & 1);
         for (int j = j0; j < j1; ++j, ++t) {
-          const uint32_t buf = t & 1, use = t >> 1;
+          const uint32_t buf = t % NS, use = t / NS;
+          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 0] = clock64();
           mbar_wait(&y_full[stage], phase);
+          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(1 * 64 + t) * 2 + 0] = clock64();
           mbar_wait(&s_empty[buf], (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t sya = smem_u32(sy + stage * Cfg::Y_BYTES);
+          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 1] = clock64();
+          const uint64_t dy = desc_advance(dy0, stage * Cfg::Y_BYTES);
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sxa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
-            const uint64_t db = make_smem_desc_sw128(sya + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
-            umma_bf16(tmem_base + buf * BN, da, db, idesc, k > 0 ? 1u : 0u);
-          }
-          umma_commit(&y_empty[stage]);
-          umma_commit(&s_full[buf]);
+          for (int k = 0; k < DP / 16; ++k)
+            umma_bf16_w(tmem_base + buf * BN, desc_advance(dx0, (k >> 2) * 16384 + (k & 3) * 32),
+                        desc_advance(dy, (k >> 2) * (BN * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u, leader);
+          umma_commit_w(&y_empty[stage], leader);
+          umma_commit_w(&s_full[buf], leader);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(x_empty);
+        umma_commit_w(x_empty, leader);
         ++xs;
       }
     }
   } else if (warp >= 4) {
-    const int e = (warp - 4) >> 2;  // epilogue group <-> TMEM buffer
-    const int q = warp & 3;
+    const int e = (warp - 4) >> 2;  // column half of every tile
+    const int q = warp & 3;         // TMEM lane quarter
     SegIter it(a.T, a.total, a.CT);
     int r, j0, j1;
     uint32_t t = 0;
@@ -189,17 +200,14 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       const long long tgt = row + a.target_offset;
       float m = -INFINITY, s = 0.f;
       for (int j = j0; j < j1; ++j, ++t) {
-        if ((int)(t & 1) != e) continue;
-        const uint32_t use = t >> 1;
-        mbar_wait(&s_full[e], use & 1);
+        const uint32_t buf = t % NS, use = t / NS;
+        mbar_wait(&s_full[buf], use & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        if (a.trace && blockIdx.x == 0 && t < 64 && q == 0 && lane == 0) a.trace[((2 + e) * 64 + t) * 2 + 0] = clock64();
+        // online (max, sum-exp) update with the 32 scores of tile columns [c*32, c*32+32)
+        auto consume = [&](float* v, int c) {
           const long long n0 = (long long)j * BN + c * 32;
-          if (n0 >= a.N) break;
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * BN + c * 32, v);
-          tmem_wait_ld();
+          if (n0 >= a.N) return;
           if (n0 + 32 > a.N) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -212,23 +220,40 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
               if (n0 + i == tgt) dg = v[i];
             a.diag[row] = dg;
           }
-          float cm = v[0];
+          // chunk maximum as a tree (4 independent chains), then one rescale of the running sum
+          float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
 #pragma unroll
-          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, v[i]);
-          const float m_new = fmaxf(m, cm * LOG2E);
-          s *= ex2f(m - m_new);
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            acc0 += ex2f(fmaf(v[i], LOG2E, -m_new));
-            acc1 += ex2f(fmaf(v[i + 1], LOG2E, -m_new));
+          for (int i = 8; i < 32; i += 4) {
+            c0 = fmaxf(c0, v[i]); c1 = fmaxf(c1, v[i + 1]); c2 = fmaxf(c2, v[i + 2]); c3 = fmaxf(c3, v[i + 3]);
           }
-          s += acc0 + acc1;
+          const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+          const float m_new = fmaxf(m, cm * LOG2E);
+          const float ms = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked so far: avoid inf - inf
+          s *= ex2f(m - ms);
+          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            acc0 += ex2f(fmaf(v[i], LOG2E, -ms));
+            acc1 += ex2f(fmaf(v[i + 1], LOG2E, -ms));
+            acc2 += ex2f(fmaf(v[i + 2], LOG2E, -ms));
+            acc3 += ex2f(fmaf(v[i + 3], LOG2E, -ms));
+          }
+          s += (acc0 + acc1) + (acc2 + acc3);
           m = m_new;
-        }
+        };
+        static_assert(BN == 128, "two 32-column chunks per epilogue group");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * 64;
+        float v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 32, v1);  // in flight while the first chunk is reduced
+        consume(v0, e * 2);
+        tmem_wait_ld();
+        consume(v1, e * 2 + 1);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[e]);
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+        if (a.trace && blockIdx.x == 0 && t < 64 && q == 0 && lane == 0) a.trace[((2 + e) * 64 + t) * 2 + 1] = clock64();
       }
       if (valid) {
         const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
@@ -243,7 +268,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, NS * BN);
   }
 }
 
@@ -317,6 +342,8 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
   a.part_m = (float*)ws;
   a.part_s = a.part_m + (size_t)s.max_slots * 2 * Bpad;
   a.diag = a.part_s + (size_t)s.max_slots * 2 * Bpad;
+  a.trace = nullptr;
+  if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
   CUtensorMap tx, ty;
   int rc = make_tmap_bf16(&tx, U, d, B, ldu, 64, 128);
   if (rc) return rc;
@@ -344,46 +371,61 @@ struct CeBwdArgs {
   const float* lse;  // indexed by user
   float* partial;    // [max_slots][XT*128][DP]
   long long slot_stride;
+  long long* trace;  // bring-up (TT_CE_TRACE): clock64 stamps of CTA 0, normally null
+  int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip E store, bit2 skip transform entirely
 };
 
 template <int DP>
 struct CeBwdCfg {
   static constexpr int BN = DP == 256 ? 64 : 128;
+  static constexpr int NS = DP == 256 ? 4 : 3;  // score-tile buffers in TMEM
+  static constexpr int LOOKAHEAD = NS - 1;      // S = X Y^T runs at most this many tiles ahead of acc += E Y
   static constexpr int KBOX = DP / 64;
   static constexpr int X_BYTES = 128 * DP * 2;
   static constexpr int Y_BYTES = BN * DP * 2;
-  static constexpr int P_BYTES = 128 * BN * 2;
-  static constexpr int STAGES = DP == 64 ? 4 : 3;
-  static constexpr int COLSTAT_BYTES = 2 * 2 * BN * 8;  // [group][double buffer][BN] float2
-  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + 2 * P_BYTES + COLSTAT_BYTES + 1024 + 256;
-  static constexpr int ACC_COL = 2 * BN;
+  static constexpr int P_BYTES = 128 * BN * 2;  // ONE E tile; its two column halves are handed over separately
+  // tile t's Y is live from S(t) until acc += E(t) Y(t) (~ one epilogue + TMA latency): a deep ring keeps the
+  // loads ahead of the UMMA warp
+  static constexpr int STAGES = DP == 64 ? 8 : (DP == 128 ? 5 : 4);
+  static constexpr int COLSTAT_BYTES = BN * 8;  // [BN] float2
+  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + P_BYTES + COLSTAT_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static constexpr int ACC_COL = NS * BN;
+  static_assert(ACC_COL + DP <= 512, "TMEM budget");
 };
 
+// Both epilogue groups work on every score tile (group e: columns [BN/2 e, BN/2 (e+1))): the tile that is
+// ready keeps all 8 epilogue warps busy while the UMMA warp already produces the next score tiles.
 template <int DP, bool COLSTATS>
 __global__ void __launch_bounds__(384, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeBwdArgs a) {
   using Cfg = CeBwdCfg<DP>;
-  constexpr int BN = Cfg::BN;
+  constexpr int BN = Cfg::BN, NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sx = smem;
   uint8_t* sy = sx + Cfg::X_BYTES;
   uint8_t* sp = sy + Cfg::STAGES * Cfg::Y_BYTES;
-  float2* scol = reinterpret_cast<float2*>(sp + 2 * Cfg::P_BYTES);
+  float2* scol = reinterpret_cast<float2*>(sp + Cfg::P_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scol) + Cfg::COLSTAT_BYTES);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 1;
   uint64_t* acc_full = bars + 2;
   uint64_t* acc_empty = bars + 3;
-  uint64_t* s_full = bars + 4;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 8;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* y_full = bars + 12;
+  uint64_t* p_full = bars + 4;   // [2]
+  uint64_t* p_empty = bars + 6;  // [2]
+  uint64_t* s_full = bars + 8;   // [NS]
+  uint64_t* s_empty = s_full + NS;
+  uint64_t* y_full = s_empty + NS;
   uint64_t* y_empty = y_full + Cfg::STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // trace layout: [role 0..3][tile 0..63][2]; role 0 = UMMA-1 issue, 1 = UMMA-2 issue, 2/3 = epilogue group 0/1
+#define CE_STAMP(role, tile, which)                                                           \
+  do {                                                                                        \
+    if (a.trace != nullptr && blockIdx.x == 0 && (tile) < 64) a.trace[((role) * 64 + (tile)) * 2 + (which)] = clock64(); \
+  } while (0)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmy);
@@ -393,11 +435,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     mbar_init(x_empty, 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 8);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+    for (int i = 0; i < 2; ++i) {  // per column half of the E tile
       mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 8);
     }
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&y_full[i], 1);
@@ -433,7 +477,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);  // S = X Y^T
       constexpr uint32_t idesc2 = make_idesc_bf16(128, DP, 0, 1);  // acc += E Y   (Y read MN-major)
       SegIter it(a.T, a.total, a.CT);
@@ -441,61 +486,74 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       int stage1 = 0, stage2 = 0;  // Y ring positions of the next UMMA-1 / UMMA-2
       uint32_t phase1 = 0;
       uint32_t t1 = 0, t2 = 0, xs = 0;
-      const uint32_t sxa = smem_u32(sx), spa = smem_u32(sp);
+      const uint64_t dx0 = make_smem_desc_sw128(smem_u32(sx), 0, 1024);          // X, K-major
+      const uint64_t dy0 = make_smem_desc_sw128(smem_u32(sy), 0, 1024);          // Y, K-major  (S = X Y^T)
+      const uint64_t dyt0 = make_smem_desc_sw128(smem_u32(sy), BN * 128, 1024);  // Y, MN-major (acc += E Y)
+      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sp), 0, 1024);          // E, K-major
       auto mma1 = [&]() {
-        const uint32_t buf = t1 & 1, use = t1 >> 1;
+        const uint32_t buf = t1 % NS, use = t1 / NS;
         mbar_wait(&y_full[stage1], phase1);
+        if (leader) CE_STAMP(0, t1, 0);
         mbar_wait(&s_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sya = smem_u32(sy + stage1 * Cfg::Y_BYTES);
+        if (leader) CE_STAMP(0, t1, 1);
+        const uint64_t dy = desc_advance(dy0, stage1 * Cfg::Y_BYTES);
 #pragma unroll
-        for (int k = 0; k < DP / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sxa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc_sw128(sya + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
-          umma_bf16(tmem_base + buf * BN, da, db, idesc1, k > 0 ? 1u : 0u);
-        }
-        umma_commit(&s_full[buf]);
+        for (int k = 0; k < DP / 16; ++k)
+          umma_bf16_w(tmem_base + buf * BN, desc_advance(dx0, (k >> 2) * 16384 + (k & 3) * 32),
+                      desc_advance(dy, (k >> 2) * (BN * 128) + (k & 3) * 32), idesc1, k > 0 ? 1u : 0u, leader);
+        umma_commit_w(&s_full[buf], leader);
         if (++stage1 == Cfg::STAGES) { stage1 = 0; phase1 ^= 1; }
         ++t1;
       };
       auto mma2 = [&](bool first) {
-        const uint32_t buf = t2 & 1, use = t2 >> 1;
-        mbar_wait(&p_full[buf], use & 1);
-        tc_fence_after();
-        const uint32_t sya = smem_u32(sy + stage2 * Cfg::Y_BYTES);
-        const uint32_t pa = spa + buf * Cfg::P_BYTES;
+        constexpr int KH = BN / 32;  // K = 16 steps per column half of E
+        const uint64_t dyt = desc_advance(dyt0, stage2 * Cfg::Y_BYTES);
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc_sw128(sya + k * 2048, BN * 128, 1024);
-          umma_bf16(tmem_base + Cfg::ACC_COL, da, db, idesc2, (!first || k > 0) ? 1u : 0u);
+        for (int h = 0; h < 2; ++h) {
+          if (h == 0 && leader) CE_STAMP(1, t2, 0);
+          mbar_wait(&p_full[h], t2 & 1);
+          tc_fence_after();
+          if (h == 1 && leader) CE_STAMP(1, t2, 1);
+#pragma unroll
+          for (int kk = 0; kk < KH; ++kk) {
+            const int k = h * KH + kk;
+            umma_bf16_w(tmem_base + Cfg::ACC_COL, desc_advance(dp0, (k >> 2) * 16384 + (k & 3) * 32),
+                        desc_advance(dyt, k * 2048), idesc2, (!first || k > 0) ? 1u : 0u, leader);
+          }
+          umma_commit_w(&p_empty[h], leader);
         }
-        umma_commit(&y_empty[stage2]);
-        umma_commit(&p_empty[buf]);
+        umma_commit_w(&y_empty[stage2], leader);
         if (++stage2 == Cfg::STAGES) stage2 = 0;
         ++t2;
       };
       while (it.next(r, j0, j1)) {
+        const int n = j1 - j0;
+        int issued = 0;
         mbar_wait(x_full, xs & 1);
-        mbar_wait(acc_empty, (xs & 1) ^ 1);
-        mma1();
-        for (int j = j0; j < j1; ++j) {
-          if (j + 1 < j1) mma1();
-          else umma_commit(x_empty);  // all S = X Y^T of this segment issued
-          mma2(j == j0);
+        for (int i = 0; i < n; ++i) {
+          while (issued < n && issued <= i + Cfg::LOOKAHEAD) {
+            mma1();
+            if (++issued == n) umma_commit_w(x_empty, leader);  // all S = X Y^T of this segment issued
+          }
+          if (i == 0) {
+            mbar_wait(acc_empty, (xs & 1) ^ 1);
+            tc_fence_after();
+          }
+          mma2(i == 0);
         }
-        umma_commit(acc_full);
+        umma_commit_w(acc_full, leader);
         ++xs;
       }
     }
   } else if (warp >= 4) {
-    const int e = (warp - 4) >> 2;
+    const int e = (warp - 4) >> 2;  // column half of every tile
     const int q = warp & 3;
     const int wg_tid = threadIdx.x - 128 - e * 128;  // 0..127 inside the epilogue group
+    constexpr int CH = BN / 64;                       // 32-column chunks per group and tile
     SegIter it(a.T, a.total, a.CT);
     int r, j0, j1;
-    uint32_t t = 0, xs = 0, my_use = 0;
-    uint8_t* my_p = sp + e * Cfg::P_BYTES;
+    uint32_t t = 0, xs = 0;
     const uint32_t prow = q * 32 + lane;  // row of the 128-row tile owned by this thread
     while (it.next(r, j0, j1)) {
       const long long row = (long long)r * 128 + prow;
@@ -507,29 +565,32 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       }
       const long long tgt = row + a.diag_shift;
       for (int j = j0; j < j1; ++j, ++t) {
-        if ((int)(t & 1) != e) continue;
-        const uint32_t use = my_use++;
-        float2* cst = scol + (e * 2 + (use & 1)) * BN;
+        const uint32_t buf = t % NS;
         if (COLSTATS) {
-          if (wg_tid < BN) {
-            const long long col = (long long)j * BN + wg_tid;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");  // previous tile's readers are done
+          if (wg_tid < BN / 2) {
+            const int cidx = e * (BN / 2) + wg_tid;
+            const long long col = (long long)j * BN + cidx;
             const bool cv = col < a.YR;
-            cst[wg_tid] = make_float2(cv ? a.g[col] : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
+            scol[cidx] = make_float2(cv ? a.g[col] : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
         }
-        mbar_wait(&s_full[e], use & 1);
-        mbar_wait(&p_empty[e], (use & 1) ^ 1);
+        mbar_wait(&s_full[buf], (t / NS) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 0);
+        // E = g (exp(S - lse) - [positive]) for the 32 columns starting at tile column c*32, in place
+        auto transform = [&](float* v, int c) {
           const long long n0 = (long long)j * BN + c * 32;
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * BN + c * 32, v);
-          tmem_wait_ld();
+          if (a.dbg & 4) return;
           if (!COLSTATS) {
+            if (a.dbg & 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
+              for (int i = 0; i < 32; ++i) v[i] = rs * fmaf(v[i], LOG2E, -rl);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
+            }
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -538,17 +599,20 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float2 cc = cst[c * 32 + i];
-              v[i] = cc.x * ex2f(fmaf(v[i], LOG2E, -cc.y));
+              const float2 cc2 = scol[c * 32 + i];
+              v[i] = cc2.x * ex2f(fmaf(v[i], LOG2E, -cc2.y));
             }
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (n0 + i == tgt) v[i] -= cst[c * 32 + i].x;
+                if (n0 + i == tgt) v[i] -= scol[c * 32 + i].x;
             }
           }
-          // bf16 pack + swizzled store: columns [c*32, c*32+32) of the P tile = 4 x 16-byte chunks
-          uint8_t* box = my_p + ((c * 32) >> 6) * 16384;
+        };
+        // bf16 pack + swizzled store: columns [c*32, c*32+32) of the E tile = 4 x 16-byte chunks
+        auto store = [&](const float* v, int c) {
+          if (a.dbg & 2) return;
+          uint8_t* box = sp + ((c * 32) >> 6) * 16384;
           const uint32_t chunk0 = ((c * 32) & 63) >> 3;
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -559,14 +623,33 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
             *reinterpret_cast<uint4*>(box + sw128_offset(prow, chunk0 + h)) = o;
           }
+        };
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * (CH * 32);
+        float v0[32];
+        tmem_ld32(taddr, v0);
+        tmem_wait_ld();
+        if (CH == 2) {
+          float v1[32];
+          tmem_ld32(taddr + 32, v1);  // in flight while the first chunk is transformed
+          transform(v0, e * CH);
+          mbar_wait(&p_empty[e], (t & 1) ^ 1);  // acc += E(t-1) Y(t-1) has consumed this half of the E tile
+          store(v0, e * CH);
+          tmem_wait_ld();
+          transform(v1, e * CH + 1);
+          store(v1, e * CH + 1);
+        } else {
+          transform(v0, e * CH);
+          mbar_wait(&p_empty[e], (t & 1) ^ 1);
+          store(v0, e * CH);
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&s_empty[e]);
+          mbar_arrive(&s_empty[buf]);
           mbar_arrive(&p_full[e]);
         }
+        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 1);
       }
       // segment accumulator -> partial slot (each group drains half of the columns)
       mbar_wait(acc_full, xs & 1);
@@ -591,6 +674,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       ++xs;
     }
   }
+#undef CE_STAMP
 
   tc_fence_before();
   __syncthreads();
@@ -651,6 +735,10 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   a.g = g; a.lse = lse;
   a.partial = (float*)ws;
   a.slot_stride = (long long)s.XT * 128 * DP;
+  a.trace = nullptr;
+  a.dbg = 0;
+  if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
+  if (const char* db = getenv("TT_CE_DBG")) a.dbg = atoi(db);
   CUtensorMap tx, ty;
   int rc = make_tmap_bf16(&tx, X, d, xr, ldx, 64, 128);
   if (rc) return rc;

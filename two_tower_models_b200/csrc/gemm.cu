@@ -65,13 +65,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
 #define TT_STAMP(slot)                                                             \
   do {                                                                             \
-    if (g.trace != nullptr && lane == 0) {                                         \
+    if (g.trace != nullptr) {                                                      \
       unsigned long long t_;                                                       \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
       g.trace[(size_t)blockIdx.x * 8 + (slot)] = t_;                               \
     }                                                                              \
   } while (0)
-  if (warp == 3) TT_STAMP(0);
+  if (warp == 3 && lane == 0) TT_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma);
@@ -93,7 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  if (warp == 3) TT_STAMP(1);
+  if (warp == 3 && lane == 0) TT_STAMP(1);
 
   const int total_work = g.m_tiles * g.n_tiles * g.splits;
 
@@ -131,12 +131,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
+      const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t da0 = g.a_mn ? make_smem_desc_sw128(s0, g.mn_lbo, g.mn_sbo) : make_smem_desc_sw128(s0, 0, 1024);
+      const uint64_t db0 = g.b_mn ? make_smem_desc_sw128(s0 + Cfg::A_BYTES, g.mn_lbo, g.mn_sbo)
+                                  : make_smem_desc_sw128(s0 + Cfg::A_BYTES, 0, 1024);
+      const uint32_t ka = g.a_mn ? g.mn_kadv : 32, kb_ = g.b_mn ? g.mn_kadv : 32;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % g.splits;
         const int kb0 = split * g.kb_per_split;
@@ -147,21 +153,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == kb0 && w == (int)blockIdx.x) TT_STAMP(2);
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (kb == kb0 && w == (int)blockIdx.x && leader) TT_STAMP(2);
+          const uint64_t da = desc_advance(da0, stage * Cfg::STAGE_BYTES);
+          const uint64_t db = desc_advance(db0, stage * Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = g.a_mn ? make_smem_desc_sw128(sa + k * g.mn_kadv, g.mn_lbo, g.mn_sbo)
-                                       : make_smem_desc_sw128(sa + k * 32, 0, 1024);
-            const uint64_t db = g.b_mn ? make_smem_desc_sw128(sb + k * g.mn_kadv, g.mn_lbo, g.mn_sbo)
-                                       : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_w(d_tmem, desc_advance(da, k * ka), desc_advance(db, k * kb_), idesc, (kb > kb0 || k > 0) ? 1u : 0u,
+                        leader);
+          umma_commit_w(&empty_bar[stage], leader);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        umma_commit_w(&tfull_bar[as], leader);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -174,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      if (warp == 4 && w == (int)blockIdx.x) TT_STAMP(3);
+      if (warp == 4 && lane == 0 && w == (int)blockIdx.x) TT_STAMP(3);
       const long long row = (long long)m_tile * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
 #pragma unroll 1
@@ -281,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (warp == 4 && w == (int)blockIdx.x) TT_STAMP(4);
+      if (warp == 4 && lane == 0 && w == (int)blockIdx.x) TT_STAMP(4);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -292,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
-  if (warp == 3) TT_STAMP(5);
+  if (warp == 3 && lane == 0) TT_STAMP(5);
 #undef TT_STAMP
 }
 

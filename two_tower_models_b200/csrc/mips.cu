@@ -226,34 +226,34 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(QT, CN, 0, 0);
       int stage = 0;
       uint32_t phase = 0, t = 0;
-      const uint32_t sqa = smem_u32(sq);
+      const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sq), 0, 1024);
+      const uint64_t dc0 = make_smem_desc_sw128(smem_u32(sc), 0, 1024);
       for (int u = 0; u < n_units; ++u) {
         int qb, j0, j1, slot;
         unit(u, qb, j0, j1, slot);
         mbar_wait(q_full, u & 1);
         for (int j = j0; j < j1; ++j, ++t) {
           mbar_wait(&c_full[stage], phase);
-          const uint32_t sca = smem_u32(sc + stage * Cfg::C_BYTES);
+          const uint64_t dc = desc_advance(dc0, stage * Cfg::C_BYTES);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             mbar_wait(&d_empty[e], (t & 1) ^ 1);
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < DP / 16; ++k) {
-              const uint64_t da = make_smem_desc_sw128(sqa + e * Cfg::Q_BYTES + (k >> 2) * (QT * 128) + (k & 3) * 32, 0, 1024);
-              const uint64_t db = make_smem_desc_sw128(sca + (k >> 2) * (CN * 128) + (k & 3) * 32, 0, 1024);
-              umma_bf16(tmem_base + e * CN, da, db, idesc, k > 0 ? 1u : 0u);
-            }
-            umma_commit(&d_full[e]);
+            for (int k = 0; k < DP / 16; ++k)
+              umma_bf16_w(tmem_base + e * CN, desc_advance(dq0, e * Cfg::Q_BYTES + (k >> 2) * (QT * 128) + (k & 3) * 32),
+                          desc_advance(dc, (k >> 2) * (CN * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u, leader);
+            umma_commit_w(&d_full[e], leader);
           }
-          umma_commit(&c_empty[stage]);
+          umma_commit_w(&c_empty[stage], leader);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(q_empty);
+        umma_commit_w(q_empty, leader);
       }
     }
   } else if (warp >= 4) {
