@@ -142,7 +142,7 @@ def test_history_model_matches_reference_golden():
     assert abs(float(loss.detach()) - float(g["out:loss"])) <= 2e-3 * abs(float(g["out:loss"]))
     for k, prm in m.named_parameters():
         assert prm.grad is not None, k
-        assert_close_fro(prm.grad, grads[k], rtol=1e-1, atol=6e-5 if prm.dim() == 1 else 2e-6, what=k)
+        assert_close_fro(prm.grad, grads[k], rtol=1e-1, atol=1e-4 if prm.dim() == 1 else 2e-6, what=k)
     top = m(b["user_id"], b["user_features"], b["user_history"])
     assert top.shape == (batch["user_id"].shape[0], 5) and top.dtype == torch.int64
 

@@ -5,7 +5,7 @@ Tolerances (fp32 reference vs bf16 tensor-core operands with fp32 accumulation, 
   rows and <= 1e-1 for the tiny golden batches (B = 32 / 96: a bf16-rounded backward operand is 2^-9
   relative per element and a 32-row reduction does not average it down);  bias gradients that are
   analytically zero (every item-side bias after the tower Linear: sum_j dS_ij = 0) are pure rounding
-  noise of the bf16-rounded dV operand (2^-9 |dV| sqrt(B) |W|) and get an absolute floor of 6e-5 per element.
+  noise of the bf16-rounded dV operand (2^-9 |dV| sqrt(B) |W|) and get an absolute floor of 1e-4 per element (bf16 rounding of E = g (P - I) breaks sum_j E_ij = 0 at the 2^-9 level).
 """
 import pytest
 import torch
@@ -15,7 +15,7 @@ from helpers import assert_close_fro, load_golden, rel_fro, section
 
 pytestmark = pytest.mark.gpu
 
-LOSS_RTOL, EMB_RTOL, GRAD_RTOL, GRAD_RTOL_TINY, GRAD_ATOL, BIAS_ATOL = 1e-3, 1e-2, 5e-2, 1e-1, 2e-6, 6e-5
+LOSS_RTOL, EMB_RTOL, GRAD_RTOL, GRAD_RTOL_TINY, GRAD_ATOL, BIAS_ATOL = 1e-3, 1e-2, 5e-2, 1e-1, 2e-6, 1e-4
 
 
 def _build_base(p, uvw, corpus=None, num_items=10):

@@ -20,48 +20,10 @@
 // warps 4-7 / 8-11 two epilogue warpgroups that alternate score tiles (TMEM buffer e <-> group e).
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "ce_common.cuh"
 #include "kernels.h"
 
 namespace tt {
-
-static constexpr float LOG2E = 1.4426950408889634f;
-static constexpr float LN2 = 0.6931471805599453f;
-
-struct SegIter {
-  long long f, f1;
-  int CT;
-  __device__ SegIter(long long T, long long total, int ct) {
-    f = (long long)blockIdx.x * T;
-    f1 = f + T < total ? f + T : total;
-    CT = ct;
-  }
-  __device__ bool next(int& r, int& j0, int& j1) {
-    if (f >= f1) return false;
-    r = (int)(f / CT);
-    j0 = (int)(f % CT);
-    long long rem = f1 - f;
-    j1 = (long long)j0 + rem < CT ? (int)(j0 + rem) : CT;
-    f += j1 - j0;
-    return true;
-  }
-};
-
-struct Sched {
-  long long T, total;
-  int XT, CT, max_slots, grid;
-};
-static Sched make_sched(long long x_rows, long long y_rows, int BN) {
-  Sched s;
-  s.XT = (int)((x_rows + 127) / 128);
-  s.CT = (int)((y_rows + BN - 1) / BN);
-  s.total = (long long)s.XT * s.CT;
-  s.grid = (int)(s.total < num_sms() ? s.total : num_sms());
-  s.T = (s.total + s.grid - 1) / s.grid;
-  s.grid = (int)((s.total + s.T - 1) / s.T);
-  s.max_slots = (int)((s.CT + s.T - 1) / s.T) + 1;
-  return s;
-}
 
 // =============================================================================================
 // Forward
@@ -362,19 +324,6 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
 // =============================================================================================
 // Backward (generic two-UMMA kernel)
 // =============================================================================================
-struct CeBwdArgs {
-  int XR, YR;            // valid rows of X / Y
-  long long diag_shift;  // element (row, col) is a positive when col == row + diag_shift
-  long long T, total;
-  int CT;
-  const float* g;    // upstream dL/dce, indexed by user
-  const float* lse;  // indexed by user
-  float* partial;    // [max_slots][XT*128][DP]
-  long long slot_stride;
-  long long* trace;  // bring-up (TT_CE_TRACE): clock64 stamps of CTA 0, normally null
-  int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip E store, bit2 skip transform entirely
-};
-
 template <int DP>
 struct CeBwdCfg {
   static constexpr int BN = DP == 256 ? 64 : 128;
@@ -744,7 +693,9 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   if (rc) return rc;
   rc = make_tmap_bf16(&ty, Y, d, yr, ldy, 64, Cfg::BN);
   if (rc) return rc;
-  rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
+  static const int version = getenv("TT_CE_BWD") ? atoi(getenv("TT_CE_BWD")) : 2;
+  if (version == 2) rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
+  else rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
   const long long n = xr * (DP / 4);
   ce_bwd_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)xr, (int)d, DP, s.T, s.CT, a.partial,

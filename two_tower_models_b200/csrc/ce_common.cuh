@@ -1,0 +1,63 @@
+// Shared pieces of the in-batch cross-entropy kernels (ce.cu, ce_bwd2.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tt {
+
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+struct SegIter {
+  long long f, f1;
+  int CT;
+  __device__ SegIter(long long T, long long total, int ct) {
+    f = (long long)blockIdx.x * T;
+    f1 = f + T < total ? f + T : total;
+    CT = ct;
+  }
+  __device__ bool next(int& r, int& j0, int& j1) {
+    if (f >= f1) return false;
+    r = (int)(f / CT);
+    j0 = (int)(f % CT);
+    long long rem = f1 - f;
+    j1 = (long long)j0 + rem < CT ? (int)(j0 + rem) : CT;
+    f += j1 - j0;
+    return true;
+  }
+};
+
+struct Sched {
+  long long T, total;
+  int XT, CT, max_slots, grid;
+};
+static inline Sched make_sched(long long x_rows, long long y_rows, int BN) {
+  Sched s;
+  s.XT = (int)((x_rows + 127) / 128);
+  s.CT = (int)((y_rows + BN - 1) / BN);
+  s.total = (long long)s.XT * s.CT;
+  s.grid = (int)(s.total < num_sms() ? s.total : num_sms());
+  s.T = (s.total + s.grid - 1) / s.grid;
+  s.grid = (int)((s.total + s.T - 1) / s.T);
+  s.max_slots = (int)((s.CT + s.T - 1) / s.T) + 1;
+  return s;
+}
+
+struct CeBwdArgs {
+  int XR, YR;            // valid rows of X / Y
+  long long diag_shift;  // element (row, col) is a positive when col == row + diag_shift
+  long long T, total;
+  int CT;
+  const float* g;    // upstream dL/dce, indexed by user
+  const float* lse;  // indexed by user
+  float* partial;    // [max_slots][XT*128][DP]
+  long long slot_stride;
+  long long* trace;  // bring-up (TT_CE_TRACE): clock64 stamps of CTA 0, normally null
+  int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip E store, bit2 skip transform entirely
+};
+
+
+// v2 backward kernel (ce_bwd2.cu): E operand and X tile in tensor memory
+int launch_ce_bwd2(int DP, bool colstats, const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid,
+                   cudaStream_t st);
+
+}  // namespace tt
