@@ -318,10 +318,12 @@ def main():
     e2e_value = B * world / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)  # no collective teardown: rank 0 still has host-only work to do
 
     # ---------------- roofline of the dominant kernel (B x N scoring) ----------------
     pk, pk_src = peaks()
@@ -374,7 +376,8 @@ def main():
     }
     print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -12,6 +12,8 @@ for _ in range(2): ops.inbatch_ce_backward_raw(U, V, B, N, d, 0, lse, g)
 torch.cuda.synchronize()
 tr = torch.zeros(4 * 64 * 2, dtype=torch.int64, device=dev)
 os.environ["TT_CE_TRACE"] = str(tr.data_ptr())
+ct = torch.zeros(148 * 4, dtype=torch.int64, device=dev)
+os.environ["TT_CE_CTA_TIMES"] = str(ct.data_ptr())
 lib = __import__("two_tower_models_b200._native", fromlist=["lib"]).lib()
 if len(sys.argv) > 2 and sys.argv[2] == "fwd":
     ops.inbatch_ce_forward_raw(U, V, B, N, d, 0)
@@ -29,6 +31,16 @@ rc = lib.tt_inbatch_ce_bwd(U.data_ptr(), U.stride(0), V.data_ptr(), V.stride(0),
                            dU.data_ptr(), dU.stride(0), None, 0, None, 0, None, 0, ws.data_ptr(), ws.numel(),
                            torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
+c = ct.cpu().view(148, 4); c = c[c[:, 0] > 0]
+c0 = int(c[:, 0].min())
+for i, nm in enumerate(["start", "setup", "work done", "exit"]):
+    col = (c[:, i] - c0).float()
+    print(f"CTA {nm:10s} ns: min {col.min():8.0f} median {col.median():8.0f} max {col.max():8.0f}")
+dur = (c[:, 2] - c[:, 1]).float()
+T = (64 * 64 + 146) // 147
+print("work us by CTA (b = has a row-tile boundary inside its range):")
+print(" ".join(f"{i}{'b' if (i * T) // 64 != ((i + 1) * T - 1) // 64 else ''}:{float(d)/1e3:.0f}" for i, d in enumerate(dur)))
+print("per-CTA work ns: min %.0f median %.0f max %.0f; slowest CTAs: %s" % (dur.min(), dur.median(), dur.max(), torch.topk(dur, 5).indices.tolist()))
 t = tr.cpu().view(4, 64, 2)
 t0 = int(t[t > 0].min())
 print("tile | S-MMA wait->issue | PV-MMA wait->issue | epilogue g0 start->end | epilogue g1 start->end   (cycles since start)")

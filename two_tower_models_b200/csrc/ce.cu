@@ -688,6 +688,8 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   a.dbg = 0;
   if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
   if (const char* db = getenv("TT_CE_DBG")) a.dbg = atoi(db);
+  a.cta_times = nullptr;
+  if (const char* ct = getenv("TT_CE_CTA_TIMES")) a.cta_times = (unsigned long long*)strtoull(ct, nullptr, 0);
   CUtensorMap tx, ty;
   int rc = make_tmap_bf16(&tx, X, d, xr, ldx, 64, 128);
   if (rc) return rc;

@@ -66,6 +66,15 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define CTA_TIME(slot)                                                          \
+  do {                                                                          \
+    if (a.cta_times != nullptr && threadIdx.x == 96) {                          \
+      unsigned long long t_;                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+      a.cta_times[(size_t)blockIdx.x * 4 + (slot)] = t_;                        \
+    }                                                                           \
+  } while (0)
+  CTA_TIME(0);
 #define CE_STAMP(role, tile, which)                                                           \
   do {                                                                                        \
     if (a.trace != nullptr && blockIdx.x == 0 && (tile) < 64) a.trace[((role) * 64 + (tile)) * 2 + (which)] = clock64(); \
@@ -99,6 +108,7 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  CTA_TIME(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -333,10 +343,13 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  CTA_TIME(2);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  CTA_TIME(3);
+#undef CTA_TIME
 }
 
 template <int DP, bool COLSTATS>

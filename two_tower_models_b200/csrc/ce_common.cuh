@@ -52,6 +52,7 @@ struct CeBwdArgs {
   float* partial;    // [max_slots][XT*128][DP]
   long long slot_stride;
   long long* trace;  // bring-up (TT_CE_TRACE): clock64 stamps of CTA 0, normally null
+  unsigned long long* cta_times;  // bring-up (TT_CE_CTA_TIMES): [grid][4] %globaltimer at start / setup / work done / exit
   int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip E store, bit2 skip transform entirely
 };
 

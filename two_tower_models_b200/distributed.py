@@ -89,6 +89,7 @@ class DataParallelContext:
         self.kernels = kernels or _CudaKernels
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._presynced = set()  # ids of parameters whose gradient is already the global sum after backward
 
     def compute_training_loss(self, model, user_embedding, item_embeddings, position, labels):
         """Sharded version of TwoTowerBaseRetrieval.compute_training_loss (reference :279-347); the
@@ -112,13 +113,33 @@ class DataParallelContext:
             return loss + additional_loss / self.world
         return loss + additional_loss
 
+    def row_exchange(self, model, table):
+        """Sparse exchange of an id-embedding table's gradient: every rank contributes its B_loc touched
+        (id, row-gradient) pairs (2 MB at B_loc = 8192, D = 128) instead of all-reducing the dense [hash, D]
+        gradient (51 MB).  Returns a callable for ops.TowerFunction, or None when the table also receives
+        other, rank-local gradient contributions (the history lookup shares the item table) - then the dense
+        all-reduce in sync_gradients handles it."""
+        if getattr(model, "user_history_encoder", None) is not None and table is model.item_id_embedding_arch.weight:
+            return None
+        self._presynced.add(id(table))
+        group, world = self.group, self.world
+
+        def exchange(ids, rows):
+            ids_all = torch.empty((world * ids.shape[0],), dtype=ids.dtype, device=ids.device)
+            rows_all = torch.empty((world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=group)
+            dist.all_gather_into_tensor(rows_all, rows, group=group)
+            return ids_all, rows_all
+
+        return exchange
+
     def sync_gradients(self, model) -> None:
         """Sum parameter gradients over the ranks (call after loss.backward()).  Dense parameters travel in
-        one flat bucket; the two embedding tables are reduced as dense [hash, D] gradients, like the
-        reference's nn.Embedding(sparse=False)."""
+        one flat bucket; embedding tables whose gradient was already exchanged row-wise (row_exchange) are
+        skipped, any other large gradient is all-reduced as a dense tensor."""
         small, big = [], []
         for p in model.parameters():
-            if p.grad is None:
+            if p.grad is None or id(p) in self._presynced:
                 continue
             (big if p.grad.numel() >= (1 << 20) else small).append(p.grad)
         if small:

@@ -133,8 +133,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn=False
     )
 
 
-def colsum(src: torch.Tensor, cols: int) -> torch.Tensor:
-    out = torch.zeros(cols, dtype=torch.float32, device=src.device)
+def colsum(src: torch.Tensor, cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] (+)= sum_r src[r, c]; a caller-provided `out` must be initialised."""
+    if out is None:
+        out = torch.zeros(cols, dtype=torch.float32, device=src.device)
     L = _native.lib()
     if src.dtype == _BF16:
         rc = L.tt_colsum(src.data_ptr(), None, src.shape[0], cols, src.stride(0), out.data_ptr(), _stream())
@@ -255,17 +257,27 @@ def _mlp_forward(feats16, F, w0_16, b0, w1_16, b1, D, out16=None, out16_col=0, o
     return H16
 
 
-def _mlp_backward(dFe16, db1, D, feats16, F, H16, w0_16, w1_16, need_dfeats=False):
+def _zero_arena(sizes, device):
+    """One zero-filled fp32 buffer carved into 16-byte aligned pieces (one memset instead of one per gradient)."""
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 3) // 4 * 4
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    return [flat[o:o + n] for o, n in zip(offs, sizes)]
+
+
+def _mlp_backward(dFe16, db1, D, feats16, F, H16, w0_16, w1_16, need_dfeats=False, bufs=None):
     """Gradients of the feature MLP given dFe (bf16 view [rows, >=D]) and its fp32 column sums db1."""
     rows = feats16.shape[0]
     hid = H16.shape[1]
     dev = feats16.device
-    dW1 = torch.zeros((D, hid), dtype=torch.float32, device=dev)
+    if bufs is None:
+        bufs = _zero_arena([D * hid, hid, hid * F], dev)
+    dW1, db0, dW0 = bufs[0].view(D, hid), bufs[1], bufs[2].view(hid, F)
     gemm(dFe16, H16, D, hid, rows, a_mn=True, b_mn=True, out32=dW1, accumulate=True)
     dH16 = torch.empty((rows, hid), dtype=_BF16, device=dev)
-    db0 = torch.zeros(hid, dtype=torch.float32, device=dev)
     gemm(dFe16, w1_16, rows, hid, D, b_mn=True, relu_mask=H16, out16=dH16, colsum=db0)  # db0 from the fp32 accumulators
-    dW0 = torch.zeros((hid, F), dtype=torch.float32, device=dev)
     gemm(dH16, feats16, hid, F, rows, a_mn=True, b_mn=True, out32=dW0, accumulate=True)
     dfeats = None
     if need_dfeats:
@@ -283,7 +295,7 @@ class TowerFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, ids, feats, extra, table, w0, b0, w1, b1, wt, bt, packed: PackedWeights, tag: str):
+    def forward(ctx, ids, feats, extra, table, w0, b0, w1, b1, wt, bt, packed: PackedWeights, tag: str, row_exchange=None):
         _need_cuda(ids, feats, table, w0, wt)
         ids = _i64c(ids)
         feats = _f32c(feats)
@@ -312,6 +324,7 @@ class TowerFunction(torch.autograd.Function):
         ctx.dims = (B, F, D, DI, E, D8, KT, table.shape[0])
         ctx.need_dfeats = feats.requires_grad
         ctx.has_extra = extra is not None
+        ctx.row_exchange = row_exchange
         emb._tt_bf16 = emb16
         return emb
 
@@ -323,12 +336,14 @@ class TowerFunction(torch.autograd.Function):
         demb16 = getattr(demb, "_tt_bf16", None)
         if demb16 is None:
             demb16 = cast_rows_bf16(_f32c(demb))
+        hid = H16.shape[1]
+        arena = _zero_arena([DI * KT, KT, DI, D * hid, hid, hid * F], dev)  # every accumulated gradient, one memset
         # tower Linear
-        dWt_p = torch.zeros((DI, KT), dtype=torch.float32, device=dev)
+        dWt_p = arena[0].view(DI, KT)
         gemm(demb16, X16, DI, KT, B, a_mn=True, b_mn=True, out32=dWt_p, accumulate=True)
-        dbt = colsum(_f32c(demb), DI)  # fp32 source: item-side bias gradients are analytically zero sums
+        dbt = colsum(_f32c(demb), DI, out=arena[2])  # fp32 source: item-side bias gradients are analytically zero sums
         dX16 = torch.empty((B, KT), dtype=_BF16, device=dev)
-        dXsum = torch.zeros(KT, dtype=torch.float32, device=dev)
+        dXsum = arena[1]
         gemm(demb16, wt_16, B, KT, DI, b_mn=True, out16=dX16, colsum=dXsum)
         if D8 == D and _r8(E) == E:
             dWt = dWt_p
@@ -336,12 +351,18 @@ class TowerFunction(torch.autograd.Function):
             parts = [dWt_p[:, :D], dWt_p[:, D8:D8 + D]] + ([dWt_p[:, 2 * D8:2 * D8 + E]] if E else [])
             dWt = torch.cat(parts, dim=1)
         # id embedding (dense gradient, duplicates accumulate)
-        dtable = scatter_add_rows(dX16, ids, D, table_rows, col_offset=0)
+        if ctx.row_exchange is not None:
+            # data parallel: all-gather the touched (ids, row gradients) of every rank and apply all of them,
+            # so the dense [hash, D] gradient is already the global sum (no 4*hash*D-byte all-reduce)
+            ids_all, rows_all = ctx.row_exchange(ids, dX16[:, :D8].contiguous())
+            dtable = scatter_add_rows(rows_all, ids_all, D, table_rows, col_offset=0)
+        else:
+            dtable = scatter_add_rows(dX16, ids, D, table_rows, col_offset=0)
         # feature MLP
         dW0, db0, dW1, db1, dfeats = _mlp_backward(dX16[:, D8:], dXsum[D8:D8 + D], D, feats16, F, H16, w0_16, w1_16,
-                                                   ctx.need_dfeats)
+                                                   ctx.need_dfeats, bufs=arena[3:6])
         dextra = dX16[:, 2 * D8:2 * D8 + E].float() if ctx.has_extra else None
-        return None, dfeats, dextra, dtable, dW0, db0, dW1, db1, dWt, dbt, None, None
+        return None, dfeats, dextra, dtable, dW0, db0, dW1, db1, dWt, dbt, None, None, None
 
 
 class EmbeddingFunction(torch.autograd.Function):

@@ -55,6 +55,11 @@ class TwoTowerBaseRetrieval(nn.Module):
         self._dp = None  # optional data-parallel context, see distributed.enable_data_parallel
         self._streams = {}  # device -> side stream for the item tower
 
+    def _row_exchange(self, table: torch.Tensor):
+        """Data parallel only: callable that all-gathers the touched embedding rows' gradients (see
+        distributed.DataParallelContext.row_exchange); None on a single GPU."""
+        return None if self._dp is None else self._dp.row_exchange(self, table)
+
     def _side_stream(self, device) -> "torch.cuda.Stream":
         st = self._streams.get(device)
         if st is None:
@@ -104,6 +109,7 @@ class TwoTowerBaseRetrieval(nn.Module):
                 user_id, user_features, self._user_tower_extra(user_history),
                 self.user_id_embedding_arch.weight, fa[0].weight, fa[0].bias, fa[2].weight, fa[2].bias,
                 self.user_tower_arch.weight, self.user_tower_arch.bias, self._packed, "user",
+                self._row_exchange(self.user_id_embedding_arch.weight),
             )
         # a subclass overrode process_user_features / get_user_embedding: honour it, keep the Linear on-device
         user_tower_input = self.process_user_features(
@@ -121,6 +127,7 @@ class TwoTowerBaseRetrieval(nn.Module):
             item_id, item_features, None,
             self.item_id_embedding_arch.weight, fa[0].weight, fa[0].bias, fa[2].weight, fa[2].bias,
             self.item_tower_arch.weight, self.item_tower_arch.bias, self._packed, "item",
+            self._row_exchange(self.item_id_embedding_arch.weight),
         )
 
     # ------------------------------------------------------------------ inference
