@@ -35,6 +35,12 @@ int tt_device_sm_count(void);
 /* Total number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 long long tt_launch_count(void);
 
+/* Optional per-kernel device timing for benchmarks: while enabled, every kernel this library launches
+ * outside of stream capture is bracketed by CUDA events on its launching stream.  tt_profile_report
+ * synchronises the device and writes one line per kernel name, "name total_ms launches\n", into buf. */
+void tt_profile_enable(int on);
+int tt_profile_report(char* buf, int64_t buf_bytes);
+
 /* ---- data movement (HBM-bound helpers) ------------------------------------------------------ */
 
 /* dst[r, 0:dst_cols] = bf16(src[r, 0:cols]) zero-padded.  Packs fp32 features / weights for the

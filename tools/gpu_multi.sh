@@ -1,7 +1,7 @@
 #!/bin/bash
+# usage: tools/gpu_multi.sh N   (N GPUs of one box)
+N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi -L | head -4
-timeout 600 python -m pytest tests/test_gpu_distributed.py -m gpu -q -p no:cacheprovider --timeout 300 2>&1 | tail -5
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-cat gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>&1 | tail -2 | cut -c1-300
+timeout 300 python -m pytest tests/test_gpu_distributed.py -m gpu -q -p no:cacheprovider --timeout 200 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+echo "bench rc=$?"; cat gpurun_out/bench_n$N.json; grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/bench_n$N.err | tail -5

@@ -1,6 +1,10 @@
 // C ABI (include/tt_b200.h) over the kernel translation units + shared host utilities.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <map>
 #include <string.h>
 
 #include "../../include/tt_b200.h"
@@ -20,6 +24,34 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing --------------------------------------------------------------------------
+struct SpanRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::atomic<int> g_profile{0};
+static std::mutex g_span_mu;
+static std::vector<SpanRec> g_spans;
+
+KernelSpan::KernelSpan(const char* name, cudaStream_t stream) : rec_(nullptr), stream_(stream) {
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  SpanRec* r = new SpanRec{name, nullptr, nullptr};
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, stream);
+  rec_ = r;
+}
+KernelSpan::~KernelSpan() {
+  if (!rec_) return;
+  SpanRec* r = static_cast<SpanRec*>(rec_);
+  cudaEventRecord(r->e1, stream_);
+  std::lock_guard<std::mutex> lk(g_span_mu);
+  g_spans.push_back(*r);
+  delete r;
+}
 
 int num_sms() {
   static int cached = 0;
@@ -77,6 +109,36 @@ int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
 const char* tt_last_error(void) { return g_err; }
 
 long long tt_launch_count(void) { return (long long)g_launches.load(); }
+
+void tt_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+
+int tt_profile_report(char* buf, int64_t buf_bytes) {
+  TT_CUDA(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<double, long long>> agg;
+  {
+    std::lock_guard<std::mutex> lk(g_span_mu);
+    for (auto& r : g_spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        auto& a = agg[r.name];
+        a.first += ms;
+        a.second += 1;
+      }
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    g_spans.clear();
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  TT_CHECK((int64_t)out.size() + 1 <= buf_bytes, "tt_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
 
 int tt_device_sm_count(void) {
   int dev = 0, n = 0;

@@ -19,6 +19,11 @@ namespace {
 
 constexpr float LOG2E_F = 1.4426950408889634f;
 
+// shared-memory row pitches (fp32 words) keep every head's slice 16-byte aligned when D and D/heads are
+// multiples of 4; the +4 staggers consecutive rows over the banks
+__host__ __device__ constexpr int round4(int x) { return (x + 3) / 4 * 4; }
+__host__ __device__ inline int attn_pitch(int D) { return 2 * D + round4(D) + 4; }
+
 __device__ __forceinline__ void load_rows_f32(float* dst, int dst_pitch, const bf16* src, long long ld, int rows,
                                               int cols, int tid, int nthreads) {
   // cols is a multiple of 8 when vec is true (16-byte aligned rows)
@@ -40,6 +45,34 @@ __device__ __forceinline__ void load_rows_f32(float* dst, int dst_pitch, const b
   }
 }
 
+// dot product of a register vector with a shared-memory row, 4 independent accumulation chains (the lanes
+// of a warp run in lock step on different rows, so instruction-level parallelism is the only latency hiding)
+template <int HD>
+__device__ __forceinline__ float dot_reg_smem(const float* a, const float* __restrict__ b, int hd) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if ((hd & 3) == 0) {  // rows are 16-byte aligned (pitch % 4 == 0): one broadcast LDS.128 per 4 FMAs
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      if (c < hd) {
+        const float4 v = *reinterpret_cast<const float4*>(b + c);
+        s0 = fmaf(a[c], v.x, s0);
+        s1 = fmaf(a[c + 1], v.y, s1);
+        s2 = fmaf(a[c + 2], v.z, s2);
+        s3 = fmaf(a[c + 3], v.w, s3);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      if (c < hd) s0 = fmaf(a[c], b[c], s0);
+      if (c + 1 < hd) s1 = fmaf(a[c + 1], b[c + 1], s1);
+      if (c + 2 < hd) s2 = fmaf(a[c + 2], b[c + 2], s2);
+      if (c + 3 < hd) s3 = fmaf(a[c + 3], b[c + 3], s3);
+    }
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -48,7 +81,7 @@ __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const bf16* __restrict__ qkv, long long ld, int H, int D, int heads, int hd, int q_rows,
                 bf16* __restrict__ out, long long ldo, float scale_log2) {
   extern __shared__ float sm[];
-  const int pitch = 3 * D + 1;  // fp32 words; odd -> the per-lane (row-strided) q loads are conflict-free
+  const int pitch = attn_pitch(D);  // fp32 words, multiple of 4: broadcast rows can be read as float4
   const long long seq = blockIdx.x;
   const bf16* base = qkv + seq * H * ld;
   load_rows_f32(sm, pitch, base, ld, H, 3 * D, threadIdx.x, blockDim.x);
@@ -66,19 +99,28 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, long long ld, int H, int D, int he
         o[c] = 0.f;
       }
       float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < H; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < HD; ++c)
-          if (c < hd) s = fmaf(q[c], K[j * pitch + c], s);
-        s *= scale_log2;
-        const float mn = fmaxf(m, s);
+      int j = 0;
+      for (; j + 1 < H; j += 2) {  // two keys per step: independent dot products, one rescale
+        const float s0 = dot_reg_smem<HD>(q, K + j * pitch, hd) * scale_log2;
+        const float s1 = dot_reg_smem<HD>(q, K + (j + 1) * pitch, hd) * scale_log2;
+        const float mn = fmaxf(m, fmaxf(s0, s1));
         const float corr = ex2f(m - mn);
-        const float p = ex2f(s - mn);
-        l = l * corr + p;
+        const float p0 = ex2f(s0 - mn), p1 = ex2f(s1 - mn);
+        l = l * corr + (p0 + p1);
 #pragma unroll
         for (int c = 0; c < HD; ++c)
-          if (c < hd) o[c] = fmaf(p, V[j * pitch + c], o[c] * corr);
+          if (c < hd) o[c] = fmaf(p1, V[(j + 1) * pitch + c], fmaf(p0, V[j * pitch + c], o[c] * corr));
+        m = mn;
+      }
+      if (j < H) {
+        const float s0 = dot_reg_smem<HD>(q, K + j * pitch, hd) * scale_log2;
+        const float mn = fmaxf(m, s0);
+        const float corr = ex2f(m - mn);
+        const float p0 = ex2f(s0 - mn);
+        l = l * corr + p0;
+#pragma unroll
+        for (int c = 0; c < HD; ++c)
+          if (c < hd) o[c] = fmaf(p0, V[j * pitch + c], o[c] * corr);
         m = mn;
       }
       const float inv = 1.f / l;
@@ -98,8 +140,8 @@ __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const bf16* __restrict__ qkv, long long ld, const bf16* __restrict__ dout, long long lddo, int H, int D,
                 int heads, int hd, int q_rows, bf16* __restrict__ dqkv, long long lddqkv, float scale, float scale_log2) {
   extern __shared__ float sm[];
-  const int pitch = 3 * D + 1;
-  const int dpitch = D + 1;
+  const int pitch = attn_pitch(D);
+  const int dpitch = attn_pitch(D) - 2 * D;  // == round4(D) + 4
   float* sdo = sm + H * pitch;                 // [q_rows][D+1] upstream gradient
   float* slse = sdo + q_rows * dpitch;         // [heads][q_rows] log2-sum-exp of the scaled scores
   float* sdelta = slse + heads * q_rows;       // [heads][q_rows] sum_c dO_ic O_ic
@@ -127,11 +169,7 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, long long ld, const bf16* __restri
         }
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < H; ++j) {
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < HD; ++c)
-            if (c < hd) s = fmaf(q[c], K[j * pitch + c], s);
-          s *= scale_log2;
+          const float s = dot_reg_smem<HD>(q, K + j * pitch, hd) * scale_log2;
           const float mn = fmaxf(m, s);
           const float corr = ex2f(m - mn);
           const float p = ex2f(s - mn);
@@ -152,13 +190,8 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, long long ld, const bf16* __restri
 #pragma unroll
         for (int c = 0; c < HD; ++c) acc[c] = 0.f;  // now dq
         for (int j = 0; j < H; ++j) {
-          float s = 0.f, dp = 0.f;
-#pragma unroll
-          for (int c = 0; c < HD; ++c)
-            if (c < hd) {
-              s = fmaf(q[c], K[j * pitch + c], s);
-              dp = fmaf(g[c], V[j * pitch + c], dp);
-            }
+          const float s = dot_reg_smem<HD>(q, K + j * pitch, hd);
+          const float dp = dot_reg_smem<HD>(g, V + j * pitch, hd);
           const float p = ex2f(s * scale_log2 - lse2);
           const float ds = p * (dp - delta) * scale;
 #pragma unroll
@@ -188,13 +221,8 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, long long ld, const bf16* __restri
           dv[c] = 0.f;
         }
         for (int i = 0; i < q_rows; ++i) {
-          float s = 0.f, dp = 0.f;
-#pragma unroll
-          for (int c = 0; c < HD; ++c)
-            if (c < hd) {
-              s = fmaf(Q[i * pitch + c], k[c], s);
-              dp = fmaf(dO[i * dpitch + c], v[c], dp);
-            }
+          const float s = dot_reg_smem<HD>(k, Q + i * pitch, hd);
+          const float dp = dot_reg_smem<HD>(v, dO + i * dpitch, hd);
           const float p = ex2f(s * scale_log2 - slse[h * q_rows + i]);
           const float ds = p * (dp - sdelta[h * q_rows + i]) * scale;
 #pragma unroll
@@ -227,7 +255,7 @@ int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long lo
   TT_CHECK(q_rows > 0 && q_rows <= H, "attn_fwd: q_rows out of range");
   const long long hd = D / heads;
   TT_CHECK(hd <= 64, "attn_fwd: head_dim %lld > 64 is not supported", hd);
-  const size_t smem = (size_t)H * (3 * D + 1) * sizeof(float);
+  const size_t smem = (size_t)H * attn_pitch((int)D) * sizeof(float);
   TT_CHECK(smem <= 200 * 1024, "attn_fwd: sequence tile H=%lld D=%lld does not fit shared memory", H, D);
   const float scale_log2 = LOG2E_F / sqrtf((float)hd);
 #define TT_LAUNCH(HDV)                                                                                           \
@@ -237,6 +265,7 @@ int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long lo
       TT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       configured = true;                                                                                         \
     }                                                                                                            \
+    KernelSpan span("attn_fwd_kernel", stream);                                                                  \
     attn_fwd_kernel<HDV><<<(unsigned)nseq, 128, smem, stream>>>((const bf16*)qkv, ld, (int)H, (int)D, (int)heads, \
                                                                 (int)hd, (int)q_rows, (bf16*)out, ldo, scale_log2); \
   } while (0)
@@ -259,7 +288,7 @@ int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, lo
   TT_CHECK(q_rows > 0 && q_rows <= H, "attn_bwd: q_rows out of range");
   const long long hd = D / heads;
   TT_CHECK(hd <= 32, "attn_bwd: head_dim %lld > 32 is not supported", hd);
-  const size_t smem = ((size_t)H * (3 * D + 1) + (size_t)q_rows * (D + 1) + 2 * (size_t)heads * q_rows) * sizeof(float);
+  const size_t smem = ((size_t)H * attn_pitch((int)D) + (size_t)q_rows * (attn_pitch((int)D) - 2 * D) + 2 * (size_t)heads * q_rows) * sizeof(float);
   TT_CHECK(smem <= 200 * 1024, "attn_bwd: sequence tile H=%lld D=%lld does not fit shared memory", H, D);
   const float scale = 1.f / sqrtf((float)hd);
   const float scale_log2 = LOG2E_F * scale;
@@ -270,6 +299,7 @@ int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, lo
       TT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       configured = true;                                                                                         \
     }                                                                                                            \
+    KernelSpan span("attn_bwd_kernel", stream);                                                                  \
     attn_bwd_kernel<HDV><<<(unsigned)nseq, 128, smem, stream>>>((const bf16*)qkv, ld, (const bf16*)dout, lddo, (int)H, \
                                                                 (int)D, (int)heads, (int)hd, (int)q_rows,        \
                                                                 (bf16*)dqkv, lddqkv, scale, scale_log2);        \

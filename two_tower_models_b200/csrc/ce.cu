@@ -280,6 +280,7 @@ static int launch_ce_fwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeF
     TT_CUDA(cudaFuncSetAttribute(ce_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  KernelSpan span("ce_fwd_kernel", st);
   ce_fwd_kernel<DP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -315,6 +316,7 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
   else if (DP == 128) rc = launch_ce_fwd<128>(tx, ty, a, s.grid, stream);
   else rc = launch_ce_fwd<256>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
+  KernelSpan span("ce_combine_kernel", stream);
   ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, a.diag, ce, lse);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -665,6 +667,7 @@ static int launch_ce_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeB
     TT_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<DP, COLSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  KernelSpan span(COLSTATS ? "ce_bwd_kernel_dV" : "ce_bwd_kernel_dU", st);
   ce_bwd_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -700,6 +703,7 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   else rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
   const long long n = xr * (DP / 4);
+  KernelSpan span("ce_bwd_reduce_kernel", stream);
   ce_bwd_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)xr, (int)d, DP, s.T, s.CT, a.partial,
                                                                          a.slot_stride, out32, ld32, (bf16*)out16, ld16);
   TT_CUDA(cudaGetLastError());

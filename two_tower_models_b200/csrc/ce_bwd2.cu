@@ -360,6 +360,7 @@ int launch2(const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, in
     TT_CUDA(cudaFuncSetAttribute(ce_bwd2_kernel<DP, COLSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  KernelSpan span(COLSTATS ? "ce_bwd2_kernel_dV" : "ce_bwd2_kernel_dU", st);
   ce_bwd2_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
   count_launch();

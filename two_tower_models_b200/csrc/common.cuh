@@ -33,6 +33,14 @@ void set_error(const char* fmt, ...);
 
 int num_sms();  // cached SM count of the current device
 void count_launch(int n = 1);  // bookkeeping for tt_launch_count()
+// Optional per-kernel device timing (tt_profile_enable): brackets ONE kernel launch with CUDA events on the
+// launching stream.  Usage:  KernelSpan span("name", stream); kernel<<<...>>>(...);   (destructor records the end)
+struct KernelSpan {
+  KernelSpan(const char* name, cudaStream_t stream);
+  ~KernelSpan();
+  void* rec_;
+  cudaStream_t stream_;
+};
 // Encode a 2-D bf16 tensor map: tensor [outer, inner] with row pitch `pitch_elems` (elements),
 // box [box_outer, box_inner], 128-byte swizzle, zero fill out of bounds.
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,

@@ -34,6 +34,7 @@ int cast_rows_bf16(const float* src, long long rows, long long cols, long long l
   if (rows == 0 || dst_cols == 0) return 0;
   TT_CHECK(((uintptr_t)dst % 4) == 0, "cast_rows_bf16: dst must be 4-byte aligned");
   const long long n = rows * ((dst_cols + 1) / 2);
+  KernelSpan span("cast_rows_kernel", stream);
   cast_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, rows, (int)cols, ld_src, (bf16*)dst, ld_dst, (int)dst_cols);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -67,6 +68,7 @@ int gather_rows_bf16(const float* table, long long table_rows, long long dim, co
                      void* dst, long long ld_dst, int* oob_flag, cudaStream_t stream) {
   if (n == 0) return 0;
   TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_bf16: bad shape");
+  KernelSpan span("gather_rows_kernel", stream);
   gather_rows_kernel<bf16><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, (bf16*)dst, ld_dst, oob_flag);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -76,6 +78,7 @@ int gather_rows_f32(const float* table, long long table_rows, long long dim, con
                     float* dst, long long ld_dst, int* oob_flag, cudaStream_t stream) {
   if (n == 0) return 0;
   TT_CHECK(table_rows > 0 && dim > 0 && ld_dst >= dim, "gather_rows_f32: bad shape");
+  KernelSpan span("gather_rows_kernel", stream);
   gather_rows_kernel<float><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(table, table_rows, (int)dim, ids, n, dst, ld_dst, oob_flag);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -104,6 +107,7 @@ int scatter_add_rows(const void* src16, const float* src32, long long ld_src, co
                      long long dim, float* table_grad, long long table_rows, cudaStream_t stream) {
   if (n == 0) return 0;
   TT_CHECK((src16 != nullptr) != (src32 != nullptr), "scatter_add_rows: exactly one source");
+  KernelSpan span("scatter_add_rows_kernel", stream);
   scatter_add_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -138,6 +142,7 @@ int colsum(const void* src16, const float* src32, long long rows, long long cols
   TT_CHECK((src16 != nullptr) != (src32 != nullptr), "colsum: exactly one source");
   const int rpb = 256;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
+  KernelSpan span("colsum_kernel", stream);
   colsum_kernel<<<grid, 256, 0, stream>>>((const bf16*)src16, src32, rows, (int)cols, ld, out, rpb);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -176,6 +181,7 @@ int history_gather_pool(const float* table, long long table_rows, long long D, c
   if (B == 0) return 0;
   TT_CHECK(H > 0 && D > 0 && ldx >= D && ldmean >= D, "history_gather_pool: bad shape");
   const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  KernelSpan span("history_gather_pool_kernel", stream);
   history_gather_pool_kernel<<<(unsigned)B, threads, 0, stream>>>(table, table_rows, (int)D, ids, (int)H, pe, (bf16*)x16, ldx, mean, ldmean, oob_flag);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -203,6 +209,7 @@ int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, l
                          long long table_rows, cudaStream_t stream) {
   if (B == 0) return 0;
   const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  KernelSpan span("history_scatter_grad_kernel", stream);
   history_scatter_grad_kernel<<<(unsigned)B, threads, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, (int)H, (int)D, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -262,6 +269,7 @@ weighted_loss_kernel(const float* __restrict__ ce, const float* __restrict__ lab
 int weighted_loss(const float* ce, const float* labels, long long ldl, const float* uvw, long long B, long long T,
                   float* loss, float* g, cudaStream_t stream) {
   TT_CHECK(B > 0 && T > 0 && ldl >= T, "weighted_loss: bad shape");
+  KernelSpan span("weighted_loss_kernel", stream);
   weighted_loss_kernel<<<1, 1024, 0, stream>>>(ce, labels, ldl, uvw, (int)B, (int)T, 1.f / (float)B, loss, g);
   TT_CUDA(cudaGetLastError());
   count_launch();

@@ -308,6 +308,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   }
   const int total = g.m_tiles * g.n_tiles * g.splits;
   const int grid = total < num_sms() ? total : num_sms();
+  KernelSpan span(g.atomic32 ? "gemm_splitk" : "gemm", stream);
   gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
   TT_CUDA(cudaGetLastError());
   count_launch();

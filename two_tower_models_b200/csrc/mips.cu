@@ -452,6 +452,7 @@ static int launch_screen(const CUtensorMap& tq, const CUtensorMap& tc, const Scr
     TT_CUDA(cudaFuncSetAttribute(mips_screen_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  KernelSpan span("mips_screen_kernel", st);
   mips_screen_kernel<DP><<<a.G, 384, Cfg::SMEM_BYTES, st>>>(tq, tc, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
@@ -489,6 +490,7 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
   f.part = a.part;
   f.q32 = Q32; f.ldq = ldq32; f.c32 = C32; f.ldc = ldc32;
   f.idx_out = idx; f.score_out = scores;
+  KernelSpan span("mips_finalize_kernel", stream);
   mips_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(f);
   TT_CUDA(cudaGetLastError());
   count_launch();

@@ -56,6 +56,24 @@ class _span:
         return False
 
 
+def profile_kernels(on: bool) -> None:
+    """Bracket every kernel the library launches (outside stream capture) with CUDA events."""
+    _native.lib().tt_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel name: (total ms, launches)} since the last report; synchronises the device."""
+    import ctypes
+
+    buf = ctypes.create_string_buffer(1 << 16)
+    _native.check(_native.lib().tt_profile_report(buf, len(buf)), "profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(n))
+    return out
+
+
 def launch_count() -> int:
     """Kernels launched by libtt_b200.so in this process so far."""
     return int(_native.lib().tt_launch_count())
