@@ -168,3 +168,44 @@ def test_history_model_reference_test_shapes():
                            torch.randint(0, 100, (B,), device="cuda"), torch.randint(0, 2, (B, 3), device="cuda").float())
     loss.backward()
     assert isinstance(loss.item(), float) and m.item_id_embedding_arch.weight.grad is not None
+
+
+ATTN_CASES = [
+    # nseq, H, D, heads, q_rows
+    (5, 50, 128, 4, 50),    # BASELINE config 3 shape: two sequences per 128-row tile, head_dim 32
+    (7, 50, 128, 4, 1),     # last encoder layer: only row 0
+    (3, 128, 64, 4, 128),   # reference unit-test shape: one sequence per tile, head_dim 16
+    (4, 17, 64, 2, 17),     # head_dim 32, odd tile tail
+    (2, 64, 128, 2, 64),    # head_dim 64
+    (301, 50, 128, 4, 50),  # more tiles than one wave of CTAs would leave idle; odd sequence count
+    (3, 10, 40, 5, 10),     # head_dim 8: CUDA-core fallback kernel
+]
+
+
+@pytest.mark.parametrize("nseq,H,D,heads,q_rows", ATTN_CASES)
+def test_attention_core_forward_backward(nseq, H, D, heads, q_rows):
+    """tt_attn_fwd / tt_attn_bwd against plain fp32 torch on the same bf16-rounded q|k|v."""
+    from two_tower_models_b200 import ops
+
+    g = torch.Generator().manual_seed(nseq * 7 + H)
+    hd = D // heads
+    qkv = (torch.randn(nseq * H, 3 * D, generator=g) * 0.7).to(torch.bfloat16)
+    dout = (torch.randn(nseq * q_rows, D, generator=g) * 0.5).to(torch.bfloat16)
+    x = qkv.float().reshape(nseq, H, 3, heads, hd).requires_grad_(True)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)  # [n, h, H, hd]
+    s = (q[:, :, :q_rows] @ k.transpose(-1, -2)) / (hd ** 0.5)
+    ref = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(nseq * q_rows, D)
+    ref.backward(dout.float())
+    dref = x.grad.reshape(nseq * H, 3 * D)
+    dev = torch.device("cuda:0")
+    pad = ops._r8(3 * D)
+    qkv_d = torch.zeros(nseq * H, pad, dtype=torch.bfloat16, device=dev)
+    qkv_d[:, :3 * D] = qkv.to(dev)
+    out = ops.attn_forward(qkv_d, nseq, H, D, heads, q_rows)
+    torch.cuda.synchronize()
+    assert rel_fro(out[:, :D].float(), ref) < 1e-2, rel_fro(out[:, :D].float(), ref)
+    do_d = torch.zeros(nseq * q_rows, ops._r8(D), dtype=torch.bfloat16, device=dev)
+    do_d[:, :D] = dout.to(dev)
+    dqkv = ops.attn_backward(qkv_d, do_d, nseq, H, D, heads, q_rows)
+    torch.cuda.synchronize()
+    assert rel_fro(dqkv[:, :3 * D].float(), dref) < 2e-2, rel_fro(dqkv[:, :3 * D].float(), dref)

@@ -10,6 +10,8 @@
 // qkv layout: [nseq*H, ld] bf16 with q at column 0, k at column D, v at column 2D, head h in columns
 // [h*hd, (h+1)*hd) of each block.  `q_rows` limits the query rows computed per sequence (the last encoder
 // layer only needs row 0: src/user_history_encoder.py:116).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -255,6 +257,9 @@ int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long lo
   TT_CHECK(q_rows > 0 && q_rows <= H, "attn_fwd: q_rows out of range");
   const long long hd = D / heads;
   TT_CHECK(hd <= 64, "attn_fwd: head_dim %lld > 64 is not supported", hd);
+  static const bool use_tc = !(getenv("TT_ATTN_TC") && atoi(getenv("TT_ATTN_TC")) == 0);
+  if (use_tc && attn_fwd_tc_supported(H, D, heads, ld, ldo, qkv, out))
+    return attn_fwd_tc(qkv, ld, nseq, H, D, heads, q_rows, out, ldo, stream);
   const size_t smem = (size_t)H * attn_pitch((int)D) * sizeof(float);
   TT_CHECK(smem <= 200 * 1024, "attn_fwd: sequence tile H=%lld D=%lld does not fit shared memory", H, D);
   const float scale_log2 = LOG2E_F / sqrtf((float)hd);
@@ -287,6 +292,9 @@ int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, lo
   TT_CHECK(nseq > 0 && H > 0 && D > 0 && heads > 0 && D % heads == 0, "attn_bwd: bad shape");
   TT_CHECK(q_rows > 0 && q_rows <= H, "attn_bwd: q_rows out of range");
   const long long hd = D / heads;
+  static const bool use_tc = !(getenv("TT_ATTN_TC") && atoi(getenv("TT_ATTN_TC")) == 0);
+  if (use_tc && attn_bwd_tc_supported(H, D, heads, ld, lddo, lddqkv, qkv, dout, dqkv))
+    return attn_bwd_tc(qkv, ld, dout, lddo, nseq, H, D, heads, q_rows, dqkv, lddqkv, stream);
   TT_CHECK(hd <= 32, "attn_bwd: head_dim %lld > 32 is not supported", hd);
   const size_t smem = ((size_t)H * attn_pitch((int)D) + (size_t)q_rows * (attn_pitch((int)D) - 2 * D) + 2 * (size_t)heads * q_rows) * sizeof(float);
   TT_CHECK(smem <= 200 * 1024, "attn_bwd: sequence tile H=%lld D=%lld does not fit shared memory", H, D);

@@ -48,6 +48,15 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
 // Only the first q_rows query rows of every sequence are computed (out / dout are [nseq*q_rows, D]).
 int attn_fwd(const void* qkv, long long ld, long long nseq, long long H, long long D, long long heads, long long q_rows,
              void* out, long long ldo, cudaStream_t stream);
+// tensor-core forward (attn_tc.cu); attn_fwd dispatches to it when the shape is supported
+bool attn_fwd_tc_supported(long long H, long long D, long long heads, long long ld, long long ldo, const void* qkv,
+                           const void* out);
+int attn_fwd_tc(const void* qkv, long long ld, long long nseq, long long H, long long D, long long heads, long long q_rows,
+                void* out, long long ldo, cudaStream_t stream);
+bool attn_bwd_tc_supported(long long H, long long D, long long heads, long long ld, long long lddo, long long lddqkv,
+                           const void* qkv, const void* dout, const void* dqkv);
+int attn_bwd_tc(const void* qkv, long long ld, const void* dout, long long lddo, long long nseq, long long H, long long D,
+                long long heads, long long q_rows, void* dqkv, long long lddqkv, cudaStream_t stream);
 int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, long long nseq, long long H, long long D,
              long long heads, long long q_rows, void* dqkv, long long lddqkv, cudaStream_t stream);
 
