@@ -79,6 +79,46 @@ int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, 
                  int64_t ld_mask, float alpha, float* c_f32, int64_t ldc_f32, void* c_bf16, int64_t ldc_bf16,
                  int32_t accumulate, int32_t split_k, float* colsum_f32, void* stream);
 
+/* Several independent GEMMs in one launch (e.g. the same layer of the user tower and of the item tower):
+ * consecutive problems that select the same tile width share a launch (up to 4), the rest follow in further
+ * launches.  Field meanings as in tt_gemm_bf16. */
+typedef struct tt_gemm_problem {
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  int64_t M, N, K;
+  const float* bias;
+  const void* relu_mask_bf16;
+  int64_t ld_mask;
+  float* c_f32;
+  int64_t ldc_f32;
+  void* c_bf16;
+  int64_t ldc_bf16;
+  float* colsum_f32;
+  float alpha;
+  int32_t a_mn_major, b_mn_major, relu, accumulate, split_k;
+} tt_gemm_problem;
+int tt_gemm_bf16_batched(const tt_gemm_problem* problems, int32_t count, void* stream);
+
+/* Batched forms of tt_cast_rows_bf16 (count <= 16) and tt_gather_rows_bf16 (count <= 8): one launch. */
+typedef struct tt_cast_problem {
+  const float* src;
+  int64_t rows, cols, ld_src;
+  void* dst_bf16;
+  int64_t ld_dst, dst_cols;
+} tt_cast_problem;
+int tt_cast_rows_bf16_batched(const tt_cast_problem* problems, int32_t count, void* stream);
+typedef struct tt_gather_problem {
+  const float* table;
+  int64_t table_rows, dim;
+  const int64_t* ids;
+  int64_t n;
+  void* dst_bf16;
+  int64_t ld_dst;
+} tt_gather_problem;
+int tt_gather_rows_bf16_batched(const tt_gather_problem* problems, int32_t count, int32_t* oob_flag, void* stream);
+
 /* ---- in-batch sampled-softmax loss ---------------------------------------------------------- */
 
 /* Scratch bytes needed by tt_inbatch_ce_fwd / _bwd for this shape on the current device. */

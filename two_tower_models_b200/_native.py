@@ -17,6 +17,33 @@ I64 = c_int64
 I32 = c_int32
 F32 = c_float
 
+class GemmProblem(ctypes.Structure):
+    """struct tt_gemm_problem (include/tt_b200.h)."""
+
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int64), ("B", c_void_p), ("ldb", c_int64),
+        ("M", c_int64), ("N", c_int64), ("K", c_int64),
+        ("bias", c_void_p), ("relu_mask_bf16", c_void_p), ("ld_mask", c_int64),
+        ("c_f32", c_void_p), ("ldc_f32", c_int64), ("c_bf16", c_void_p), ("ldc_bf16", c_int64),
+        ("colsum_f32", c_void_p), ("alpha", c_float),
+        ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("relu", c_int32), ("accumulate", c_int32), ("split_k", c_int32),
+    ]
+
+
+class CastProblem(ctypes.Structure):
+    """struct tt_cast_problem."""
+
+    _fields_ = [("src", c_void_p), ("rows", c_int64), ("cols", c_int64), ("ld_src", c_int64),
+                ("dst_bf16", c_void_p), ("ld_dst", c_int64), ("dst_cols", c_int64)]
+
+
+class GatherProblem(ctypes.Structure):
+    """struct tt_gather_problem."""
+
+    _fields_ = [("table", c_void_p), ("table_rows", c_int64), ("dim", c_int64), ("ids", c_void_p), ("n", c_int64),
+                ("dst_bf16", c_void_p), ("ld_dst", c_int64)]
+
+
 # name -> (restype, argtypes); mirrors include/tt_b200.h one to one
 SIGNATURES = {
     "tt_abi_version": (I32, []),
@@ -31,6 +58,9 @@ SIGNATURES = {
     "tt_scatter_add_rows": (I32, [P, P, I64, P, I64, I64, P, I64, P]),
     "tt_colsum": (I32, [P, P, I64, I64, I64, P, P]),
     "tt_gemm_bf16": (I32, [P, I64, I32, P, I64, I32, I64, I64, I64, P, I32, P, I64, F32, P, I64, P, I64, I32, I32, P, P]),
+    "tt_gemm_bf16_batched": (I32, [P, I32, P]),
+    "tt_cast_rows_bf16_batched": (I32, [P, I32, P]),
+    "tt_gather_rows_bf16_batched": (I32, [P, I32, P, P]),
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, I64, P]),

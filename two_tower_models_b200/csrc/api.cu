@@ -182,6 +182,34 @@ int tt_gemm_bf16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, 
   return gemm_bf16(d, S(stream));
 }
 
+int tt_gemm_bf16_batched(const tt_gemm_problem* pr, int32_t count, void* stream) {
+  TT_CHECK(pr != nullptr && count >= 1 && count <= 16, "tt_gemm_bf16_batched: 1..16 problems");
+  GemmDesc d[16];
+  for (int i = 0; i < count; ++i) {
+    d[i].A = pr[i].A; d[i].lda = pr[i].lda; d[i].a_mn_major = pr[i].a_mn_major;
+    d[i].B = pr[i].B; d[i].ldb = pr[i].ldb; d[i].b_mn_major = pr[i].b_mn_major;
+    d[i].M = pr[i].M; d[i].N = pr[i].N; d[i].K = pr[i].K;
+    d[i].bias = pr[i].bias; d[i].relu = pr[i].relu; d[i].relu_mask = pr[i].relu_mask_bf16; d[i].ld_mask = pr[i].ld_mask;
+    d[i].alpha = pr[i].alpha;
+    d[i].c32 = pr[i].c_f32; d[i].ldc32 = pr[i].ldc_f32; d[i].c16 = pr[i].c_bf16; d[i].ldc16 = pr[i].ldc_bf16;
+    d[i].accumulate = pr[i].accumulate; d[i].split_k = pr[i].split_k; d[i].colsum = pr[i].colsum_f32;
+  }
+  return gemm_bf16_batched(d, count, S(stream));
+}
+int tt_cast_rows_bf16_batched(const tt_cast_problem* pr, int32_t count, void* stream) {
+  TT_CHECK(pr != nullptr && count >= 1 && count <= 16, "tt_cast_rows_bf16_batched: 1..16 problems");
+  CastProblem c[16];
+  for (int i = 0; i < count; ++i) c[i] = CastProblem{pr[i].src, pr[i].rows, pr[i].cols, pr[i].ld_src, pr[i].dst_bf16, pr[i].ld_dst, pr[i].dst_cols};
+  return cast_rows_bf16_batched(c, count, S(stream));
+}
+int tt_gather_rows_bf16_batched(const tt_gather_problem* pr, int32_t count, int32_t* oob_flag, void* stream) {
+  TT_CHECK(pr != nullptr && count >= 1 && count <= 8, "tt_gather_rows_bf16_batched: 1..8 problems");
+  GatherProblem g[8];
+  for (int i = 0; i < count; ++i)
+    g[i] = GatherProblem{pr[i].table, pr[i].table_rows, pr[i].dim, (const long long*)pr[i].ids, pr[i].n, pr[i].dst_bf16, pr[i].ld_dst};
+  return gather_rows_bf16_batched(g, count, oob_flag, S(stream));
+}
+
 int64_t tt_inbatch_ce_workspace_bytes(int64_t B, int64_t N, int64_t d) {
   return (int64_t)inbatch_ce_workspace_bytes(B, N, d);
 }

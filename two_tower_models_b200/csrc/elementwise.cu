@@ -136,10 +136,70 @@ __global__ void colsum_kernel(const bf16* __restrict__ s16, const float* __restr
     atomicAdd(out + c, t);
   }
 }
+// vectorised variant: a thread owns 8 consecutive columns (one 16-byte bf16 load / two fp32 float4 loads per row),
+// a block covers 256 columns x its share of the rows; rows are read as full contiguous segments.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ src, long long rows, int cols, long long ld, float* __restrict__ out,
+                  long long rows_per_block) {
+  __shared__ float red[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < cols) {
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      if (sizeof(T) == 2) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+        const bf16* b = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(b[e]);
+      } else {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + r * ld + c0);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + r * ld + c0 + 4);
+        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+        acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ty][tx][e] = acc[e];
+  __syncthreads();
+  if (ty == 0 && c0 < cols) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][tx][e];
+      atomicAdd(out + c0 + e, t);
+    }
+  }
+}
+
 int colsum(const void* src16, const float* src32, long long rows, long long cols, long long ld, float* out,
            cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
   TT_CHECK((src16 != nullptr) != (src32 != nullptr), "colsum: exactly one source");
+  const void* base = src16 ? src16 : (const void*)src32;
+  const bool vec = (cols % 8 == 0) && (ld % 8 == 0) && (((uintptr_t)base) % 16 == 0);
+  if (vec) {
+    const unsigned gx = (unsigned)((cols + 255) / 256);
+    long long gy = (4ll * num_sms() + gx - 1) / gx;            // ~4 blocks per SM in total
+    long long rpb = (rows + gy - 1) / gy;
+    rpb = rpb < 64 ? 64 : (rpb + 7) / 8 * 8;                   // at least 8 rows per thread-row
+    gy = (rows + rpb - 1) / rpb;
+    dim3 grid(gx, (unsigned)gy);
+    KernelSpan span("colsum_kernel", stream);
+    if (src16) colsum_vec_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)src16, rows, (int)cols, ld, out, rpb);
+    else colsum_vec_kernel<float><<<grid, 256, 0, stream>>>(src32, rows, (int)cols, ld, out, rpb);
+    TT_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const int rpb = 256;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
   KernelSpan span("colsum_kernel", stream);
@@ -271,6 +331,92 @@ int weighted_loss(const float* ce, const float* labels, long long ldl, const flo
   TT_CHECK(B > 0 && T > 0 && ldl >= T, "weighted_loss: bad shape");
   KernelSpan span("weighted_loss_kernel", stream);
   weighted_loss_kernel<<<1, 1024, 0, stream>>>(ce, labels, ldl, uvw, (int)B, (int)T, 1.f / (float)B, loss, g);
+  TT_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched variants: several independent cast / gather problems in one launch (both towers, all weights)
+// ---------------------------------------------------------------------------------------------
+struct CastBatch {
+  CastProblem p[16];
+  int n;
+  int block_start[17];
+};
+__global__ void cast_rows_batched_kernel(const __grid_constant__ CastBatch b) {
+  int p = 0;
+  while ((int)blockIdx.x >= b.block_start[p + 1]) ++p;
+  const CastProblem& c = b.p[p];
+  const int half = (int)((c.dst_cols + 1) / 2);
+  const long long idx = (long long)(blockIdx.x - b.block_start[p]) * blockDim.x + threadIdx.x;
+  const long long r = idx / half;
+  const int cp = (int)(idx % half) * 2;
+  if (r >= c.rows) return;
+  const float* s = c.src + r * c.ld_src;
+  bf16* d = reinterpret_cast<bf16*>(c.dst) + r * c.ld_dst;
+  const float a0 = cp < c.cols ? s[cp] : 0.f;
+  const float a1 = cp + 1 < c.cols ? s[cp + 1] : 0.f;
+  if (cp + 1 < c.dst_cols) *reinterpret_cast<__nv_bfloat162*>(d + cp) = __floats2bfloat162_rn(a0, a1);
+  else d[cp] = __float2bfloat16(a0);
+}
+int cast_rows_bf16_batched(const CastProblem* probs, int n, cudaStream_t stream) {
+  TT_CHECK(n >= 1 && n <= 16, "cast_rows_bf16_batched: 1..16 problems");
+  CastBatch b;
+  b.n = n;
+  b.block_start[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const CastProblem& c = probs[i];
+    TT_CHECK(c.cols <= c.dst_cols && c.dst_cols <= c.ld_dst && (c.ld_dst % 2) == 0 && ((uintptr_t)c.dst % 4) == 0,
+             "cast_rows_bf16_batched: bad shape in problem %d", i);
+    b.p[i] = c;
+    const long long work = c.rows * ((c.dst_cols + 1) / 2);
+    b.block_start[i + 1] = b.block_start[i] + (int)((work + 255) / 256);
+  }
+  for (int i = n; i < 16; ++i) b.block_start[i + 1] = b.block_start[n];
+  if (b.block_start[n] == 0) return 0;
+  KernelSpan span("cast_rows_batched_kernel", stream);
+  cast_rows_batched_kernel<<<b.block_start[n], 256, 0, stream>>>(b);
+  TT_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+struct GatherBatch {
+  GatherProblem p[8];
+  int n;
+  int block_start[9];
+};
+__global__ void gather_rows_batched_kernel(const __grid_constant__ GatherBatch b, int* oob_flag) {
+  int p = 0;
+  while ((int)blockIdx.x >= b.block_start[p + 1]) ++p;
+  const GatherProblem& g = b.p[p];
+  const long long w = ((long long)(blockIdx.x - b.block_start[p]) * blockDim.x + threadIdx.x) >> 5;  // one warp per row
+  const int lane = threadIdx.x & 31;
+  if (w >= g.n) return;
+  long long id = g.ids[w];
+  if (id < 0 || id >= g.table_rows) {
+    if (oob_flag && lane == 0) atomicExch(oob_flag, 1);
+    id = id < 0 ? 0 : g.table_rows - 1;
+  }
+  const float* src = g.table + id * g.dim;
+  bf16* dst = reinterpret_cast<bf16*>(g.dst) + w * g.ld_dst;
+  for (int c = lane; c < g.dim; c += 32) dst[c] = __float2bfloat16(src[c]);
+}
+int gather_rows_bf16_batched(const GatherProblem* probs, int n, int* oob_flag, cudaStream_t stream) {
+  TT_CHECK(n >= 1 && n <= 8, "gather_rows_bf16_batched: 1..8 problems");
+  GatherBatch b;
+  b.n = n;
+  b.block_start[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    TT_CHECK(probs[i].table_rows > 0 && probs[i].dim > 0 && probs[i].ld_dst >= probs[i].dim, "gather_rows_bf16_batched: bad shape");
+    b.p[i] = probs[i];
+    b.block_start[i + 1] = b.block_start[i] + (int)((probs[i].n * 32 + 255) / 256);
+  }
+  for (int i = n; i < 8; ++i) b.block_start[i + 1] = b.block_start[n];
+  if (b.block_start[n] == 0) return 0;
+  KernelSpan span("gather_rows_batched_kernel", stream);
+  gather_rows_batched_kernel<<<b.block_start[n], 256, 0, stream>>>(b, oob_flag);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -36,7 +36,17 @@ struct GemmArgs {
   int vec32, vec16, vecmask;
   int mn_lbo, mn_sbo, mn_kadv;  // MN-major descriptor strides (bytes)
   float* colsum;                 // optional [N] fp32, += column sums of the final C values
-  unsigned long long* trace;     // bring-up: per-CTA %globaltimer stamps (TT_GEMM_TRACE), normally null
+};
+
+// Up to MAXP independent problems per launch (e.g. the same layer of the user tower and of the item tower):
+// the work items of all problems form one list that the persistent CTAs stride over, so two half-empty
+// launches become one launch that fills the SMs, and a dependent chain of small GEMMs is half as long.
+static constexpr int MAXP = 4;
+struct GemmBatch {
+  CUtensorMap ta[MAXP], tb[MAXP];
+  GemmArgs g[MAXP];
+  int n;
+  int work_start[MAXP + 1];
 };
 
 template <int BN>
@@ -51,7 +61,7 @@ struct GemmCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ GemmBatch bt) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,19 +73,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-#define TT_STAMP(slot)                                                             \
-  do {                                                                             \
-    if (g.trace != nullptr) {                                                      \
-      unsigned long long t_;                                                       \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
-      g.trace[(size_t)blockIdx.x * 8 + (slot)] = t_;                               \
-    }                                                                              \
-  } while (0)
-  if (warp == 3 && lane == 0) TT_STAMP(0);
-
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma);
-    tma_prefetch_desc(&tmb);
+    for (int p = 0; p < bt.n; ++p) {
+      tma_prefetch_desc(&bt.ta[p]);
+      tma_prefetch_desc(&bt.tb[p]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -93,17 +95,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  if (warp == 3 && lane == 0) TT_STAMP(1);
-
-  const int total_work = g.m_tiles * g.n_tiles * g.splits;
+  const int total_work = bt.work_start[bt.n];
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w % g.splits;
-        const int t = w / g.splits;
+        int p = 0;
+        while (w >= bt.work_start[p + 1]) ++p;
+        const GemmArgs& g = bt.g[p];
+        const CUtensorMap* tma = &bt.ta[p];
+        const CUtensorMap* tmb = &bt.tb[p];
+        const int lw = w - bt.work_start[p];
+        const int split = lw % g.splits;
+        const int t = lw / g.splits;
         const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
@@ -113,18 +119,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (!g.a_mn) {
-            tma_load_2d(sa, &tma, &full_bar[stage], kb * BK, m_tile * BM);
+            tma_load_2d(sa, tma, &full_bar[stage], kb * BK, m_tile * BM);
           } else {
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b)
-              tma_load_2d(sa + b * (BK * 128), &tma, &full_bar[stage], m_tile * BM + b * 64, kb * BK);
+              tma_load_2d(sa + b * (BK * 128), tma, &full_bar[stage], m_tile * BM + b * 64, kb * BK);
           }
           if (!g.b_mn) {
-            tma_load_2d(sb, &tmb, &full_bar[stage], kb * BK, n_tile * BN);
+            tma_load_2d(sb, tmb, &full_bar[stage], kb * BK, n_tile * BN);
           } else {
 #pragma unroll
             for (int b = 0; b < BN / 64; ++b)
-              tma_load_2d(sb + b * (BK * 128), &tmb, &full_bar[stage], n_tile * BN + b * 64, kb * BK);
+              tma_load_2d(sb + b * (BK * 128), tmb, &full_bar[stage], n_tile * BN + b * 64, kb * BK);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -133,18 +139,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
   } else if (warp == 1) {
     {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
       const uint32_t leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       const uint32_t s0 = smem_u32(smem);
-      const uint64_t da0 = g.a_mn ? make_smem_desc_sw128(s0, g.mn_lbo, g.mn_sbo) : make_smem_desc_sw128(s0, 0, 1024);
-      const uint64_t db0 = g.b_mn ? make_smem_desc_sw128(s0 + Cfg::A_BYTES, g.mn_lbo, g.mn_sbo)
-                                  : make_smem_desc_sw128(s0 + Cfg::A_BYTES, 0, 1024);
-      const uint32_t ka = g.a_mn ? g.mn_kadv : 32, kb_ = g.b_mn ? g.mn_kadv : 32;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w % g.splits;
+        int p = 0;
+        while (w >= bt.work_start[p + 1]) ++p;
+        const GemmArgs& g = bt.g[p];
+        const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+        const uint64_t da0 = g.a_mn ? make_smem_desc_sw128(s0, g.mn_lbo, g.mn_sbo) : make_smem_desc_sw128(s0, 0, 1024);
+        const uint64_t db0 = g.b_mn ? make_smem_desc_sw128(s0 + Cfg::A_BYTES, g.mn_lbo, g.mn_sbo)
+                                    : make_smem_desc_sw128(s0 + Cfg::A_BYTES, 0, 1024);
+        const uint32_t ka = g.a_mn ? g.mn_kadv : 32, kb_ = g.b_mn ? g.mn_kadv : 32;
+        const int lw = w - bt.work_start[p];
+        const int split = lw % g.splits;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -153,7 +163,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == kb0 && w == (int)blockIdx.x && leader) TT_STAMP(2);
           const uint64_t da = desc_advance(da0, stage * Cfg::STAGE_BYTES);
           const uint64_t db = desc_advance(db0, stage * Cfg::STAGE_BYTES);
 #pragma unroll
@@ -172,11 +181,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     int as = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int t = w / g.splits;
+      int p = 0;
+      while (w >= bt.work_start[p + 1]) ++p;
+      const GemmArgs& g = bt.g[p];
+      const int t = (w - bt.work_start[p]) / g.splits;
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      if (warp == 4 && lane == 0 && w == (int)blockIdx.x) TT_STAMP(3);
       const long long row = (long long)m_tile * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
 #pragma unroll 1
@@ -283,7 +294,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (warp == 4 && lane == 0 && w == (int)blockIdx.x) TT_STAMP(4);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -294,52 +304,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
-  if (warp == 3 && lane == 0) TT_STAMP(5);
-#undef TT_STAMP
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+static int launch_gemm(const GemmBatch& bt, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
     TT_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int total = g.m_tiles * g.n_tiles * g.splits;
+  const int total = bt.work_start[bt.n];
   const int grid = total < num_sms() ? total : num_sms();
-  KernelSpan span(g.atomic32 ? "gemm_splitk" : "gemm", stream);
-  gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+  KernelSpan span(bt.g[0].atomic32 ? "gemm_splitk" : "gemm", stream);
+  gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(bt);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
+static int pick_bn(const GemmDesc& d) {
+  // fewest padded columns first; then the widest tile that still gives ~one CTA per SM, else the narrowest
+  int BN = 64;
+  const long long m_tiles = (d.M + BM - 1) / BM;
+  long long best_pad = -1;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
+    if (best_pad < 0 || padded < best_pad) best_pad = padded;
+  }
+  bool found = false;
+  for (int i = 0; i < 3 && !found; ++i) {
+    const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
+    if (padded != best_pad) continue;
+    BN = cand[i];  // ends at the narrowest candidate with minimal padding
+    if (m_tiles * (padded / cand[i]) * 4 >= 3ll * num_sms()) found = true;
+  }
+  return BN;
+}
+
+// validate one problem and fill its kernel arguments / tensor maps; `share` = problems in the same launch
+static int prepare(const GemmDesc& d, int BN, int share, GemmArgs& g, CUtensorMap& ta, CUtensorMap& tb) {
   TT_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", d.M, d.N, d.K);
   TT_CHECK(d.A && d.B, "gemm: null operand");
   TT_CHECK((d.lda % 8) == 0 && (d.ldb % 8) == 0, "gemm: operand pitches must be multiples of 8 elements (lda=%lld ldb=%lld)", d.lda, d.ldb);
   TT_CHECK(((uintptr_t)d.A % 16) == 0 && ((uintptr_t)d.B % 16) == 0, "gemm: operands must be 16-byte aligned");
   TT_CHECK(d.c32 || d.c16 || d.colsum, "gemm: no output");
-
-  int BN = 64;
-  {  // fewest padded columns first; then the widest tile that still gives ~one CTA per SM, else the narrowest
-    const long long m_tiles = (d.M + BM - 1) / BM;
-    long long best_pad = -1;
-    const int cand[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
-      const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
-      if (best_pad < 0 || padded < best_pad) best_pad = padded;
-    }
-    bool found = false;
-    for (int i = 0; i < 3 && !found; ++i) {
-      const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
-      if (padded != best_pad) continue;
-      BN = cand[i];  // ends at the narrowest candidate with minimal padding
-      if (m_tiles * (padded / cand[i]) * 4 >= 3ll * num_sms()) found = true;
-    }
-  }
-  GemmArgs g;
+  TT_CHECK(!(d.accumulate && (d.bias || d.relu || d.relu_mask || d.c16 || d.colsum)),
+           "gemm: split-K accumulation only supports a plain fp32 output");
   g.M = (int)d.M; g.N = (int)d.N; g.K = (int)d.K;
   g.a_mn = d.a_mn_major; g.b_mn = d.b_mn_major;
   g.m_tiles = (int)((d.M + BM - 1) / BM);
@@ -349,7 +361,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   if (d.accumulate) {
     splits = d.split_k;
     if (splits <= 0) {
-      const int tiles = g.m_tiles * g.n_tiles;
+      const int tiles = g.m_tiles * g.n_tiles * share;
       splits = tiles >= num_sms() ? 1 : (num_sms() + tiles - 1) / tiles;
       const int max_useful = g.kb_total / 8 > 0 ? g.kb_total / 8 : 1;  // >= 8 k-blocks per CTA: fewer atomics
       if (splits > max_useful) splits = max_useful;
@@ -368,28 +380,46 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t stream) {
   g.vec16 = d.c16 && (d.ldc16 % 8 == 0) && ((uintptr_t)d.c16 % 16 == 0);
   g.vecmask = d.relu_mask && (d.ld_mask % 8 == 0) && ((uintptr_t)d.relu_mask % 16 == 0);
   g.mn_lbo = BK * 128; g.mn_sbo = 1024; g.mn_kadv = 2048;
-  if (const char* dbg = getenv("TT_DBG_MN")) {  // bring-up knob: "lbo,sbo,kadv"
-    sscanf(dbg, "%d,%d,%d", &g.mn_lbo, &g.mn_sbo, &g.mn_kadv);
-  }
-  g.trace = nullptr;
-  if (const char* tr = getenv("TT_GEMM_TRACE")) g.trace = (unsigned long long*)strtoull(tr, nullptr, 0);
-  TT_CHECK(!(d.accumulate && (d.bias || d.relu || d.relu_mask || d.c16 || d.colsum)),
-           "gemm: split-K accumulation only supports a plain fp32 output");
-
-  CUtensorMap ta, tb;
   int rc;
   if (!d.a_mn_major) rc = make_tmap_bf16(&ta, d.A, d.K, d.M, d.lda, 64, BM);
   else               rc = make_tmap_bf16(&ta, d.A, d.M, d.K, d.lda, 64, BK);
   if (rc) return rc;
   if (!d.b_mn_major) rc = make_tmap_bf16(&tb, d.B, d.K, d.N, d.ldb, 64, BN);
   else               rc = make_tmap_bf16(&tb, d.B, d.N, d.K, d.ldb, 64, BK);
-  if (rc) return rc;
+  return rc;
+}
 
+static int launch_bn(int BN, const GemmBatch& bt, cudaStream_t stream) {
   switch (BN) {
-    case 64:  return launch_gemm<64>(ta, tb, g, stream);
-    case 128: return launch_gemm<128>(ta, tb, g, stream);
-    default:  return launch_gemm<256>(ta, tb, g, stream);
+    case 64:  return launch_gemm<64>(bt, stream);
+    case 128: return launch_gemm<128>(bt, stream);
+    default:  return launch_gemm<256>(bt, stream);
   }
 }
+
+int gemm_bf16_batched(const GemmDesc* d, int n, cudaStream_t stream) {
+  TT_CHECK(n >= 1, "gemm: empty batch");
+  int i = 0;
+  while (i < n) {  // greedy groups of consecutive problems with the same tile width and accumulation mode
+    const int BN = pick_bn(d[i]);
+    int j = i + 1;
+    while (j < n && j - i < MAXP && pick_bn(d[j]) == BN && (d[j].accumulate != 0) == (d[i].accumulate != 0)) ++j;
+    GemmBatch bt;
+    bt.n = j - i;
+    bt.work_start[0] = 0;
+    for (int p = 0; p < bt.n; ++p) {
+      const int rc = prepare(d[i + p], BN, bt.n, bt.g[p], bt.ta[p], bt.tb[p]);
+      if (rc) return rc;
+      bt.work_start[p + 1] = bt.work_start[p] + bt.g[p].m_tiles * bt.g[p].n_tiles * bt.g[p].splits;
+    }
+    for (int p = bt.n; p < MAXP; ++p) bt.work_start[p + 1] = bt.work_start[bt.n];
+    const int rc = launch_bn(BN, bt, stream);
+    if (rc) return rc;
+    i = j;
+  }
+  return 0;
+}
+
+int gemm_bf16(const GemmDesc& d, cudaStream_t stream) { return gemm_bf16_batched(&d, 1, stream); }
 
 }  // namespace tt

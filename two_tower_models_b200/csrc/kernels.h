@@ -27,6 +27,8 @@ struct GemmDesc {
   float* colsum = nullptr;  // optional [N] fp32: += column sums of the final C (caller initialises)
 };
 int gemm_bf16(const GemmDesc& d, cudaStream_t stream);
+// n independent problems; consecutive problems with the same tile width share one launch (up to 4)
+int gemm_bf16_batched(const GemmDesc* d, int n, cudaStream_t stream);
 
 // In-batch sampled-softmax cross entropy.
 size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d);
@@ -59,6 +61,23 @@ int attn_bwd_tc(const void* qkv, long long ld, const void* dout, long long lddo,
                 long long heads, long long q_rows, void* dqkv, long long lddqkv, cudaStream_t stream);
 int attn_bwd(const void* qkv, long long ld, const void* dout, long long lddo, long long nseq, long long H, long long D,
              long long heads, long long q_rows, void* dqkv, long long lddqkv, cudaStream_t stream);
+
+struct CastProblem {
+  const float* src;
+  long long rows, cols, ld_src;
+  void* dst;  // bf16
+  long long ld_dst, dst_cols;
+};
+struct GatherProblem {
+  const float* table;
+  long long table_rows, dim;
+  const long long* ids;
+  long long n;
+  void* dst;  // bf16
+  long long ld_dst;
+};
+int cast_rows_bf16_batched(const CastProblem* probs, int n, cudaStream_t stream);
+int gather_rows_bf16_batched(const GatherProblem* probs, int n, int* oob_flag, cudaStream_t stream);
 
 // Elementwise / gather / scatter helpers (elementwise.cu)
 int cast_rows_bf16(const float* src, long long rows, long long cols, long long ld_src, void* dst, long long ld_dst,

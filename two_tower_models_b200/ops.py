@@ -734,3 +734,199 @@ class HistoryEncoderFunction(torch.autograd.Function):
         if dense_x:
             dtable = dtable.reshape(src_shape)
         return (None, dtable, None, None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------
+# batched launches: the same step of several towers in ONE kernel launch
+# --------------------------------------------------------------------------------------------
+def gemm_batched(problems) -> None:
+    """problems: list of dicts with the keyword arguments of `gemm` plus A, B, M, N, K."""
+    n = len(problems)
+    arr = (_native.GemmProblem * n)()
+    for i, p in enumerate(problems):
+        g = arr[i]
+        A, B = p["A"], p["B"]
+        g.A, g.lda, g.B, g.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+        g.M, g.N, g.K = p["M"], p["N"], p["K"]
+        g.a_mn_major, g.b_mn_major = int(p.get("a_mn", False)), int(p.get("b_mn", False))
+        bias, mask = p.get("bias"), p.get("relu_mask")
+        g.bias = _ptr(bias)
+        g.relu = int(p.get("relu", False))
+        g.relu_mask_bf16 = _ptr(mask)
+        g.ld_mask = mask.stride(0) if mask is not None else 0
+        o32, o16 = p.get("out32"), p.get("out16")
+        g.c_f32, g.ldc_f32 = _ptr(o32), (o32.stride(0) if o32 is not None else 0)
+        g.c_bf16, g.ldc_bf16 = _ptr(o16), (o16.stride(0) if o16 is not None else 0)
+        g.colsum_f32 = _ptr(p.get("colsum"))
+        g.alpha = p.get("alpha", 1.0)
+        g.accumulate, g.split_k = int(p.get("accumulate", False)), p.get("split_k", 0)
+    _native.check(_native.lib().tt_gemm_bf16_batched(arr, n, _stream()), "gemm_bf16_batched")
+
+
+def cast_batched(items) -> None:
+    """items: list of (src fp32 2-D, src_col0, cols, out bf16 2-D, col_offset, dst_cols); one launch per 16 items."""
+    for i0 in range(0, len(items), 16):
+        chunk = items[i0:i0 + 16]
+        arr = (_native.CastProblem * len(chunk))()
+        for c, (src, src_col0, cols, out, col_offset, dst_cols) in zip(arr, chunk):
+            c.src, c.rows, c.cols, c.ld_src = src.data_ptr() + 4 * src_col0, src.shape[0], cols, src.stride(0)
+            c.dst_bf16, c.ld_dst, c.dst_cols = out.data_ptr() + 2 * col_offset, out.stride(0), dst_cols
+        _native.check(_native.lib().tt_cast_rows_bf16_batched(arr, len(chunk), _stream()), "cast_rows_bf16_batched")
+
+
+def gather_batched(items) -> None:
+    """items: list of (table fp32, ids int64, out bf16, col_offset)."""
+    arr = (_native.GatherProblem * len(items))()
+    for g, (table, ids, out, col_offset) in zip(arr, items):
+        g.table, g.table_rows, g.dim = table.data_ptr(), table.shape[0], table.shape[1]
+        g.ids, g.n = ids.data_ptr(), ids.numel()
+        g.dst_bf16, g.ld_dst = out.data_ptr() + 2 * col_offset, out.stride(0)
+    flag = _oob_flag(items[0][0].device)
+    _native.check(_native.lib().tt_gather_rows_bf16_batched(arr, len(items), flag.data_ptr(), _stream()),
+                  "gather_rows_bf16_batched")
+    _maybe_check_ids(items[0][0].device, "gather_rows")
+
+
+def _stage_weight(packed: PackedWeights, key, param, casts, segments=None) -> torch.Tensor:
+    """bf16 operand copy of `param` from the cache; when stale, its cast is appended to `casts` (run later
+    as part of one batched launch) instead of being launched here."""
+    ver = (param.data_ptr(), param._version, tuple(param.shape), str(param.device))
+    hit = packed._cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    rows, cols = param.shape
+    src = _f32c(param.detach())
+    if segments is None:
+        segments = [(0, cols, 0)]
+    width = max(d0 + _r8(c) for (_, c, d0) in segments)
+    if hit is not None and hit[1].shape == (rows, width) and hit[1].device == param.device:
+        out = hit[1]
+    else:
+        out = torch.zeros((rows, width), dtype=_BF16, device=param.device)
+    for (s0, c, d0) in segments:
+        casts.append((src, s0, c, out, d0, c))
+    packed._cache[key] = (ver, out)
+    return out
+
+
+class TowerSetFunction(torch.autograd.Function):
+    """Several towers ([id_emb | MLP(feats) | extra] -> Linear, reference :112-219) advanced in lock step: every
+    stage (casts, gathers, each GEMM layer, each gradient GEMM) is ONE launch covering all towers, which halves
+    the dependent chain of small launch-latency-bound kernels of a training step and fills the SMs.
+
+    apply(specs, packed, *tensors): specs = [(tag, row_exchange)] per tower; tensors = 10 per tower:
+    ids, feats, extra (or None), table, w0, b0, w1, b1, wt, bt.  Returns one fp32 embedding per tower
+    (bf16 shadow attached as `_tt_bf16`)."""
+
+    @staticmethod
+    def forward(ctx, specs, packed: PackedWeights, *tensors):
+        T = len(specs)
+        tw, casts, gathers = [], [], []
+        with torch.no_grad():
+            for t in range(T):
+                ids, feats, extra, table, w0, b0, w1, b1, wt, bt = tensors[10 * t: 10 * t + 10]
+                tag = specs[t][0]
+                _need_cuda(ids, feats, table, w0, wt)
+                ids, feats = _i64c(ids), _f32c(feats)
+                B, F = feats.shape
+                D, DI, hid = table.shape[1], wt.shape[0], w0.shape[0]
+                E = 0 if extra is None else extra.shape[1]
+                D8 = _r8(D)
+                KT = 2 * D8 + _r8(E)
+                assert wt.shape[1] == 2 * D + E, "tower weight does not match [id_emb | feat_emb | extra]"
+                segs = [(0, D, 0), (D, D, D8)] + ([(2 * D, E, 2 * D8)] if E else [])
+                dev = feats.device
+                d = dict(ids=ids, B=B, F=F, D=D, DI=DI, E=E, D8=D8, KT=KT, hid=hid, table_rows=table.shape[0],
+                         need_dfeats=feats.requires_grad, has_extra=extra is not None, row_exchange=specs[t][1])
+                d["w0_16"] = _stage_weight(packed, tag + ".w0", w0, casts)
+                d["w1_16"] = _stage_weight(packed, tag + ".w1", w1, casts)
+                d["wt_16"] = _stage_weight(packed, tag + ".wt", wt, casts, segments=segs)
+                d["feats16"] = torch.empty((B, _r8(F)), dtype=_BF16, device=dev)
+                casts.append((feats, 0, F, d["feats16"], 0, _r8(F)))
+                dense = (D8 == D) and (_r8(E) == E)
+                d["X16"] = (torch.empty if dense else torch.zeros)((B, KT), dtype=_BF16, device=dev)
+                if E:
+                    casts.append((_f32c(extra), 0, E, d["X16"], 2 * D8, E))
+                gathers.append((_f32c(table), ids, d["X16"], 0))
+                d["H16"] = torch.empty((B, hid), dtype=_BF16, device=dev)
+                d["emb"] = torch.empty((B, DI), dtype=torch.float32, device=dev)
+                d["emb16"] = torch.empty((B, _r8(DI)), dtype=_BF16, device=dev)
+                d["b0"], d["b1"], d["bt"] = _f32c(b0), _f32c(b1), _f32c(bt)
+                tw.append(d)
+            cast_batched(casts)
+            gather_batched(gathers)
+            gemm_batched([dict(A=d["feats16"], B=d["w0_16"], M=d["B"], N=d["hid"], K=d["F"], bias=d["b0"], relu=True,
+                               out16=d["H16"]) for d in tw])
+            gemm_batched([dict(A=d["H16"], B=d["w1_16"], M=d["B"], N=d["D"], K=d["hid"], bias=d["b1"],
+                               out16=d["X16"][:, d["D8"]:]) for d in tw])
+            gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
+                               out16=d["emb16"]) for d in tw])
+        ctx.tw = tw
+        outs = []
+        for d in tw:
+            d["emb"]._tt_bf16 = d["emb16"]
+            outs.append(d["emb"])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dembs):
+        tw = ctx.tw
+        T = len(tw)
+        dev = dembs[0].device
+        casts = []
+        for d, demb in zip(tw, dembs):
+            if demb is None:  # this tower's embedding did not reach the loss
+                demb = torch.zeros_like(d["emb"])
+            d16 = getattr(demb, "_tt_bf16", None)
+            demb = _f32c(demb)
+            if d16 is None:
+                d16 = torch.empty((d["B"], _r8(d["DI"])), dtype=_BF16, device=dev)
+                casts.append((demb, 0, d["DI"], d16, 0, _r8(d["DI"])))
+            d["demb"], d["demb16"] = demb, d16
+        if casts:
+            cast_batched(casts)
+        # every accumulated gradient of every tower lives in one zero-filled arena (one memset)
+        sizes = []
+        for d in tw:
+            sizes += [d["DI"] * d["KT"], d["KT"], d["DI"], d["D"] * d["hid"], d["hid"], d["hid"] * d["F"]]
+        arena = _zero_arena(sizes, dev)
+        for t, d in enumerate(tw):
+            a = arena[6 * t: 6 * t + 6]
+            d["dWt_p"], d["dXsum"], d["dbt"] = a[0].view(d["DI"], d["KT"]), a[1], a[2]
+            d["dW1"], d["db0"], d["dW0"] = a[3].view(d["D"], d["hid"]), a[4], a[5].view(d["hid"], d["F"])
+            d["dX16"] = torch.empty((d["B"], d["KT"]), dtype=_BF16, device=dev)
+            d["dH16"] = torch.empty((d["B"], d["hid"]), dtype=_BF16, device=dev)
+            colsum(d["demb"], d["DI"], out=d["dbt"])  # fp32 source: analytically-zero sums stay at fp32 noise
+        # dX = demb Wt (+ fp32 column sums = bias gradient of the second MLP layer)
+        gemm_batched([dict(A=d["demb16"], B=d["wt_16"], M=d["B"], N=d["KT"], K=d["DI"], b_mn=True, out16=d["dX16"],
+                           colsum=d["dXsum"]) for d in tw])
+        # weight gradients of the tower Linear and of MLP layer 1 (split-K over the batch)
+        gemm_batched([dict(A=d["demb16"], B=d["X16"], M=d["DI"], N=d["KT"], K=d["B"], a_mn=True, b_mn=True,
+                           out32=d["dWt_p"], accumulate=True) for d in tw] +
+                     [dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
+                           out32=d["dW1"], accumulate=True) for d in tw])
+        # dH = (dFe W1) masked by ReLU (+ column sums = bias gradient of layer 0)
+        gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["w1_16"], M=d["B"], N=d["hid"], K=d["D"], b_mn=True,
+                           relu_mask=d["H16"], out16=d["dH16"], colsum=d["db0"]) for d in tw])
+        gemm_batched([dict(A=d["dH16"], B=d["feats16"], M=d["hid"], N=d["F"], K=d["B"], a_mn=True, b_mn=True,
+                           out32=d["dW0"], accumulate=True) for d in tw])
+        grads = []
+        for d in tw:
+            D, D8, E, KT = d["D"], d["D8"], d["E"], d["KT"]
+            if D8 == D and _r8(E) == E:
+                dWt = d["dWt_p"]
+            else:
+                parts = [d["dWt_p"][:, :D], d["dWt_p"][:, D8:D8 + D]] + ([d["dWt_p"][:, 2 * D8:2 * D8 + E]] if E else [])
+                dWt = torch.cat(parts, dim=1)
+            if d["row_exchange"] is not None:
+                ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :D8].contiguous())
+                dtable = scatter_add_rows(rows_all, ids_all, D, d["table_rows"], col_offset=0)
+            else:
+                dtable = scatter_add_rows(d["dX16"], d["ids"], D, d["table_rows"], col_offset=0)
+            dfeats = None
+            if d["need_dfeats"]:
+                dfeats = torch.empty((d["B"], d["F"]), dtype=torch.float32, device=dev)
+                gemm(d["dH16"], d["w0_16"], d["B"], d["F"], d["hid"], b_mn=True, out32=dfeats)
+            dextra = d["dX16"][:, 2 * D8:2 * D8 + E].float() if d["has_extra"] else None
+            grads += [None, dfeats, dextra, dtable, d["dW0"], d["db0"], d["dW1"], d["dXsum"][D8:D8 + D], dWt, d["dbt"]]
+        return (None, None, *grads)

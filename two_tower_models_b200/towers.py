@@ -15,6 +15,7 @@ import os
 from . import ops
 
 _OVERLAP_TOWERS = os.environ.get("TT_B200_OVERLAP_TOWERS", "1") == "1"
+_BATCH_TOWERS = os.environ.get("TT_B200_BATCH_TOWERS", "1") == "1"
 
 
 class TwoTowerBaseRetrieval(nn.Module):
@@ -193,7 +194,19 @@ class TwoTowerBaseRetrieval(nn.Module):
         stream (forked from / joined to the caller's stream; autograd replays the same split in backward):
         each tower is a chain of small launch-latency-bound kernels that fills half of the SMs at most.
         """
-        if _OVERLAP_TOWERS and item_id.is_cuda:
+        if _BATCH_TOWERS and item_id.is_cuda and self._fused_user_tower_ok():
+            # both towers advance in lock step: every stage is one launch covering the user and the item side
+            fu, fi = self.user_features_arch, self.item_features_arch
+            user_embedding, item_embeddings = ops.TowerSetFunction.apply(
+                [("user", self._row_exchange(self.user_id_embedding_arch.weight)),
+                 ("item", self._row_exchange(self.item_id_embedding_arch.weight))],
+                self._packed,
+                user_id, user_features, self._user_tower_extra(user_history), self.user_id_embedding_arch.weight,
+                fu[0].weight, fu[0].bias, fu[2].weight, fu[2].bias, self.user_tower_arch.weight, self.user_tower_arch.bias,
+                item_id, item_features, None, self.item_id_embedding_arch.weight,
+                fi[0].weight, fi[0].bias, fi[2].weight, fi[2].bias, self.item_tower_arch.weight, self.item_tower_arch.bias,
+            )
+        elif _OVERLAP_TOWERS and item_id.is_cuda:
             cur = torch.cuda.current_stream(item_id.device)
             side = self._side_stream(item_id.device)
             side.wait_stream(cur)
