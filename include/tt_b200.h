@@ -133,11 +133,13 @@ int tt_inbatch_ce_fwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64
                       void* stream);
 
 /* Backward for upstream g[i] = dL/dce[i]:  dS = g_i (softmax(S)_ij - [j == i+off]);  dU = dS V;  dV = dS^T U.
- * Any of dU_f32/dU_bf16/dV_f32/dV_bf16 may be NULL (a NULL pair skips that pass). */
+ * Any of dU_f32/dU_bf16/dV_f32/dV_bf16 may be NULL (a NULL pair skips that pass).
+ * dU_colsum / dV_colsum (may be NULL, d <= 128): [d] fp32, += column sums of dU / dV (the bias gradients of the
+ * tower Linear layers that produced U and V); the caller initialises them. */
 int tt_inbatch_ce_bwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N, int64_t d,
                       int64_t target_offset, const float* lse, const float* g, float* dU_f32, int64_t lddu,
                       void* dU_bf16, int64_t lddu16, float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      float* dU_colsum, float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Value-weighted mean of the per-row loss with the identity debias hook (reference
  * src/two_tower_base_retrieval.py:322-343): nuv_i = sum_t labels[i,t] * weights[t]; w_i = max(nuv_i, 1e-6) /

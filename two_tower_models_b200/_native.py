@@ -63,7 +63,7 @@ SIGNATURES = {
     "tt_gather_rows_bf16_batched": (I32, [P, I32, P, P]),
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
-    "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, I64, P]),
+    "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, P, P, I64, P]),
     "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),

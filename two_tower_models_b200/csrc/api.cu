@@ -219,10 +219,10 @@ int tt_inbatch_ce_fwd(const void* U, int64_t ldu, const void* V, int64_t ldv, in
 }
 int tt_inbatch_ce_bwd(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
                       int64_t target_offset, const float* lse, const float* g, float* dU, int64_t lddu, void* dU16,
-                      int64_t lddu16, float* dV, int64_t lddv, void* dV16, int64_t lddv16, void* ws, int64_t ws_bytes,
-                      void* stream) {
+                      int64_t lddu16, float* dV, int64_t lddv, void* dV16, int64_t lddv16, float* dU_colsum,
+                      float* dV_colsum, void* ws, int64_t ws_bytes, void* stream) {
   return inbatch_ce_bwd(U, ldu, V, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16, lddv16,
-                        ws, (size_t)ws_bytes, S(stream));
+                        dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream));
 }
 
 int tt_weighted_loss(const float* ce, const float* labels, int64_t ldl, const float* weights, int64_t B, int64_t T,

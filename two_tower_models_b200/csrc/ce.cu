@@ -268,8 +268,8 @@ size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d) {
   size_t a = fwd_ws_bytes(make_sched(B, N, 128), Bpad);
   size_t b = bwd_ws_bytes(make_sched(B, N, BNb), DP);
   size_t c = bwd_ws_bytes(make_sched(N, B, BNb), DP);
-  size_t m = a > b ? a : b;
-  return (m > c ? m : c) + 256;
+  const size_t bw = (b + 255) / 256 * 256 + c;  // the two backward passes use disjoint regions
+  return (a > bw ? a : bw) + 256;
 }
 
 template <int DP>
@@ -635,26 +635,53 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   }
 }
 
-// out[row, c] = sum over the slots that touched row's tile
-__global__ void ce_bwd_reduce_kernel(int rows, int d, int DP, long long T, int CT, const float* partial,
-                                     long long slot_stride, float* out32, long long ld32, bf16* out16, long long ld16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// out[row, c] = sum over the slots that touched row's tile; one launch handles up to two results (dU and dV) and
+// optionally accumulates the fp32 column sums of each result (= the bias gradient of the tower Linear above it).
+struct ReduceJob {
+  int rows, d, CT;
+  long long T, slot_stride;
+  const float* partial;
+  float* out32;
+  long long ld32;
+  bf16* out16;
+  long long ld16;
+  float* colsum;  // [d] or null; caller initialises
+  int blocks;
+};
+__global__ void __launch_bounds__(256)
+ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
+  __shared__ float red[1024];  // [rows of the block][DP columns]
+  const bool second = (int)blockIdx.x >= j0.blocks;
+  const ReduceJob& j = second ? j1 : j0;
+  const long long idx = (long long)(blockIdx.x - (second ? j0.blocks : 0)) * blockDim.x + threadIdx.x;
   const int cpr = DP / 4;
   const long long row = idx / cpr;
   const int c = (int)(idx % cpr) * 4;
-  if (row >= rows) return;
-  const long long r = row / 128;
-  const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int sl = 0; sl <= last - first; ++sl) {
-    const float4 p = *reinterpret_cast<const float4*>(partial + (long long)sl * slot_stride + row * DP + c);
-    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  if (row < j.rows) {
+    const long long r = row / 128;
+    const int first = (int)((r * j.CT) / j.T), last = (int)(((r + 1) * j.CT - 1) / j.T);
+    for (int sl = 0; sl <= last - first; ++sl) {
+      const float4 p = *reinterpret_cast<const float4*>(j.partial + (long long)sl * j.slot_stride + row * DP + c);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int i = 0; i < 4; ++i) {
+      if (c + i < j.d) {
+        if (j.out32) j.out32[row * j.ld32 + c + i] = vals[i];
+        if (j.out16) j.out16[row * j.ld16 + c + i] = __float2bfloat16(vals[i]);
+      }
+    }
   }
-  const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
-  for (int i = 0; i < 4; ++i) {
-    if (c + i < d) {
-      if (out32) out32[row * ld32 + c + i] = vals[i];
-      if (out16) out16[row * ld16 + c + i] = __float2bfloat16(vals[i]);
+  if (j.colsum != nullptr && cpr <= 32) {  // block = (256 / cpr) rows x cpr column groups
+    const int rpb = 256 / cpr, ry = threadIdx.x / cpr, cx = threadIdx.x % cpr;
+    float* rr = red + ry * DP + cx * 4;
+    rr[0] = acc.x; rr[1] = acc.y; rr[2] = acc.z; rr[3] = acc.w;
+    __syncthreads();
+    if (threadIdx.x < DP && threadIdx.x < j.d) {
+      float t = 0.f;
+      for (int i = 0; i < rpb; ++i) t += red[i * DP + threadIdx.x];
+      atomicAdd(j.colsum + threadIdx.x, t);
     }
   }
 }
@@ -677,7 +704,8 @@ static int launch_ce_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeB
 template <int DP>
 static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr, const void* Y, long long ldy,
                        long long yr, long long d, long long diag_shift, const float* g, const float* lse, float* out32,
-                       long long ld32, void* out16, long long ld16, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
+                       ReduceJob& job, cudaStream_t stream) {
   using Cfg = CeBwdCfg<DP>;
   const Sched s = make_sched(xr, yr, Cfg::BN);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
@@ -702,39 +730,52 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   if (version == 2) rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
   else rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
-  const long long n = xr * (DP / 4);
-  KernelSpan span("ce_bwd_reduce_kernel", stream);
-  ce_bwd_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)xr, (int)d, DP, s.T, s.CT, a.partial,
-                                                                         a.slot_stride, out32, ld32, (bf16*)out16, ld16);
-  TT_CUDA(cudaGetLastError());
-  count_launch();
+  job.rows = (int)xr; job.d = (int)d; job.CT = s.CT; job.T = s.T; job.slot_stride = a.slot_stride;
+  job.partial = a.partial; job.out32 = out32; job.ld32 = ld32; job.out16 = (bf16*)out16; job.ld16 = ld16;
+  job.colsum = colsum;
+  job.blocks = (int)((xr * (DP / 4) + 255) / 256);
   return 0;
 }
 
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
-                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, void* ws, size_t ws_bytes,
-                   cudaStream_t stream) {
+                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, float* dU_colsum,
+                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_bwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_bwd: embedding dim %lld > 256 is not supported", d);
   TT_CHECK((ldu % 8) == 0 && (ldv % 8) == 0 && ((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0,
            "inbatch_ce_bwd: operands need 16-byte aligned rows");
+  TT_CHECK(ws_bytes >= inbatch_ce_workspace_bytes(B, N, d) - 256, "inbatch_ce_bwd: workspace too small");
   const int DP = pick_dp(d);
+  const int BNb = DP == 256 ? 64 : 128;
+  const size_t offB = (bwd_ws_bytes(make_sched(B, N, BNb), DP) + 255) / 256 * 256;  // region of the dV pass
+  ReduceJob ja, jb;
+  ja.blocks = jb.blocks = 0;
+  ja.rows = jb.rows = 0;
   int rc = 0;
+  const bool wantU = dU || dU16, wantV = dV || dV16;
 #define TT_PASS(DPV)                                                                                                 \
   do {                                                                                                               \
-    if (dU || dU16)                                                                                                  \
-      rc = ce_bwd_pass<DPV>(false, U, ldu, B, V, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, lddu16, ws,       \
-                            ws_bytes, stream);                                                                       \
-    if (rc == 0 && (dV || dV16))                                                                                     \
-      rc = ce_bwd_pass<DPV>(true, V, ldv, N, U, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, lddv16, ws,       \
-                            ws_bytes, stream);                                                                       \
+    if (wantU)                                                                                                       \
+      rc = ce_bwd_pass<DPV>(false, U, ldu, B, V, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, lddu16, dU_colsum, ws, \
+                            offB, ja, stream);                                                                       \
+    if (rc == 0 && wantV)                                                                                            \
+      rc = ce_bwd_pass<DPV>(true, V, ldv, N, U, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, lddv16, dV_colsum,  \
+                            (char*)ws + offB, ws_bytes - offB, jb, stream);                                          \
   } while (0)
   if (DP == 64) TT_PASS(64);
   else if (DP == 128) TT_PASS(128);
   else TT_PASS(256);
 #undef TT_PASS
-  return rc;
+  if (rc) return rc;
+  if (!wantU) { ja = jb; jb.blocks = 0; }
+  if (ja.blocks + jb.blocks == 0) return 0;
+  if (DP > 128) { ja.colsum = nullptr; jb.colsum = nullptr; }  // handled by the caller (tt_colsum) for wide rows
+  KernelSpan span("ce_bwd_reduce_kernel", stream);
+  ce_bwd_reduce_kernel<<<(unsigned)(ja.blocks + jb.blocks), 256, 0, stream>>>(ja, jb, DP);
+  TT_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 }  // namespace tt

@@ -36,6 +36,7 @@ struct GemmArgs {
   int vec32, vec16, vecmask;
   int mn_lbo, mn_sbo, mn_kadv;  // MN-major descriptor strides (bytes)
   float* colsum;                 // optional [N] fp32, += column sums of the final C values
+  int dbg;                       // bring-up (TT_GEMM_DBG): bit0 skip global stores, bit1 skip bias shuffles
 };
 
 // Up to MAXP independent problems per launch (e.g. the same layer of the user tower and of the item tower):
@@ -183,7 +184,7 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int p = 0;
       while (w >= bt.work_start[p + 1]) ++p;
-      const GemmArgs& g = bt.g[p];
+      const GemmArgs g = bt.g[p];  // registers: the chunk loop below must not re-read kernel parameters
       const int t = (w - bt.work_start[p]) / g.splits;
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       mbar_wait(&tfull_bar[as], aphase);
@@ -198,7 +199,20 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
         // operands of the epilogue are fetched while the TMEM load is in flight
         const bool full = (n0 + 32 <= g.N);
-        const float bias_l = (g.bias != nullptr && n0 + lane < g.N) ? __ldg(g.bias + n0 + lane) : 0.f;
+        // bias of the chunk: 8 independent broadcast 16-byte loads (a per-element __ldg + add gets serialised by
+        // ptxas, a shuffle broadcast costs as much crossbar time as the stores)
+        float bias_r[32];
+        const bool vbias = g.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+        if (vbias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+            bias_r[4 * j] = b4.x; bias_r[4 * j + 1] = b4.y; bias_r[4 * j + 2] = b4.z; bias_r[4 * j + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias_r[j] = (g.bias != nullptr && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+        }
         uint4 mv[4];
         const bool vmask = g.mask != nullptr && row_ok && full && g.vecmask;
         if (vmask) {
@@ -209,7 +223,7 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = fmaf(v[j], g.alpha, __shfl_sync(0xffffffffu, bias_l, j));
+          float x = fmaf(v[j], g.alpha, bias_r[j]);
           if (g.relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
@@ -229,7 +243,7 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
               if (n0 + j < g.N && !(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
           }
         }
-        if (row_ok) {
+        if (row_ok && !(g.dbg & 1)) {
           if (g.c32 != nullptr) {
             float* cp = g.c32 + row * g.ldc32 + n0;
             if (g.atomic32 && full && g.vec32) {
@@ -380,6 +394,7 @@ static int prepare(const GemmDesc& d, int BN, int share, GemmArgs& g, CUtensorMa
   g.vec16 = d.c16 && (d.ldc16 % 8 == 0) && ((uintptr_t)d.c16 % 16 == 0);
   g.vecmask = d.relu_mask && (d.ld_mask % 8 == 0) && ((uintptr_t)d.relu_mask % 16 == 0);
   g.mn_lbo = BK * 128; g.mn_sbo = 1024; g.mn_kadv = 2048;
+  g.dbg = getenv("TT_GEMM_DBG") ? atoi(getenv("TT_GEMM_DBG")) : 0;
   int rc;
   if (!d.a_mn_major) rc = make_tmap_bf16(&ta, d.A, d.K, d.M, d.lda, 64, BM);
   else               rc = make_tmap_bf16(&ta, d.A, d.M, d.K, d.lda, 64, BK);

@@ -37,8 +37,8 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
 // dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
-                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, void* ws, size_t ws_bytes,
-                   cudaStream_t stream);
+                   long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, float* dU_colsum,
+                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // MIPS: top-k of Q C^T per query row.
 size_t mips_workspace_bytes(long long Q, long long C, long long d, long long k);

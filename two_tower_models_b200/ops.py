@@ -494,7 +494,8 @@ def inbatch_ce_forward_raw(U16, V16, B, N, d, target_offset=0):
     return ce, lse
 
 
-def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True):
+def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True, colsums=None):
+    """colsums: optional zero-initialised fp32 [2, d] receiving the column sums of dU and dV (d <= 128)."""
     dev = U16.device
     dU = torch.empty((B, d), dtype=torch.float32, device=dev)
     dV = torch.empty((N, d), dtype=torch.float32, device=dev)
@@ -507,7 +508,9 @@ def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=
                 U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, target_offset,
                 lse.data_ptr(), g.data_ptr(), dU.data_ptr(), dU.stride(0), _ptr(dU16),
                 dU16.stride(0) if want_bf16 else 0, dV.data_ptr(), dV.stride(0), _ptr(dV16),
-                dV16.stride(0) if want_bf16 else 0, ws.data_ptr(), ws.numel(), _stream()),
+                dV16.stride(0) if want_bf16 else 0,
+                None if colsums is None else colsums.data_ptr(), None if colsums is None else colsums.data_ptr() + 4 * d,
+                ws.data_ptr(), ws.numel(), _stream()),
             "inbatch_ce_bwd",
         )
     return dU, dV, dU16, dV16
@@ -538,9 +541,13 @@ class InBatchCEFunction(torch.autograd.Function):
     def backward(ctx, g):
         U16, V16, lse = ctx.saved_tensors
         B, N, d, off = ctx.dims
-        dU, dV, dU16, dV16 = inbatch_ce_backward_raw(U16, V16, B, N, d, off, lse, _f32c(g))
+        cs = torch.zeros((2, d), dtype=torch.float32, device=g.device) if d <= 128 else None
+        dU, dV, dU16, dV16 = inbatch_ce_backward_raw(U16, V16, B, N, d, off, lse, _f32c(g), colsums=cs)
         dU._tt_bf16 = dU16
         dV._tt_bf16 = dV16
+        if cs is not None:  # fp32 column sums = bias gradients of the tower Linears, saves two reduction launches
+            dU._tt_colsum = cs[0]
+            dV._tt_colsum = cs[1]
         return dU, dV, None
 
 
@@ -787,6 +794,17 @@ def gather_batched(items) -> None:
     _maybe_check_ids(items[0][0].device, "gather_rows")
 
 
+_aux_streams = {}
+
+
+def _aux_stream(device) -> "torch.cuda.Stream":
+    st = _aux_streams.get(device)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _aux_streams[device] = st
+    return st
+
+
 def _stage_weight(packed: PackedWeights, key, param, casts, segments=None) -> torch.Tensor:
     """bf16 operand copy of `param` from the cache; when stale, its cast is appended to `casts` (run later
     as part of one batched launch) instead of being launched here."""
@@ -853,6 +871,18 @@ class TowerSetFunction(torch.autograd.Function):
                 d["emb16"] = torch.empty((B, _r8(DI)), dtype=_BF16, device=dev)
                 d["b0"], d["b1"], d["bt"] = _f32c(b0), _f32c(b1), _f32c(bt)
                 tw.append(d)
+            # dense embedding-table gradients (the reference's nn.Embedding(sparse=False) semantics) need a zero
+            # fill of hash x D floats per step: start it now on a side stream, it overlaps the forward kernels
+            zero_jobs = [d for t, d in enumerate(tw) if ctx.needs_input_grad[2 + 10 * t + 3]]
+            if zero_jobs:
+                cur = torch.cuda.current_stream(zero_jobs[0]["feats16"].device)
+                aux = _aux_stream(zero_jobs[0]["feats16"].device)
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    for d in zero_jobs:
+                        d["dtable"] = torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=cur.device)
+                    ev = torch.cuda.Event()
+                    ev.record(aux)
             cast_batched(casts)
             gather_batched(gathers)
             gemm_batched([dict(A=d["feats16"], B=d["w0_16"], M=d["B"], N=d["hid"], K=d["F"], bias=d["b0"], relu=True,
@@ -861,6 +891,10 @@ class TowerSetFunction(torch.autograd.Function):
                                out16=d["X16"][:, d["D8"]:]) for d in tw])
             gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
                                out16=d["emb16"]) for d in tw])
+            if zero_jobs:  # join the side stream again (the fills are long done: they ran beside the kernels above)
+                cur.wait_event(ev)
+                for d in zero_jobs:
+                    d["dtable"].record_stream(cur)
         ctx.tw = tw
         outs = []
         for d in tw:
@@ -882,7 +916,7 @@ class TowerSetFunction(torch.autograd.Function):
             if d16 is None:
                 d16 = torch.empty((d["B"], _r8(d["DI"])), dtype=_BF16, device=dev)
                 casts.append((demb, 0, d["DI"], d16, 0, _r8(d["DI"])))
-            d["demb"], d["demb16"] = demb, d16
+            d["demb"], d["demb16"], d["demb_colsum"] = demb, d16, getattr(demb, "_tt_colsum", None)
         if casts:
             cast_batched(casts)
         # every accumulated gradient of every tower lives in one zero-filled arena (one memset)
@@ -896,7 +930,10 @@ class TowerSetFunction(torch.autograd.Function):
             d["dW1"], d["db0"], d["dW0"] = a[3].view(d["D"], d["hid"]), a[4], a[5].view(d["hid"], d["F"])
             d["dX16"] = torch.empty((d["B"], d["KT"]), dtype=_BF16, device=dev)
             d["dH16"] = torch.empty((d["B"], d["hid"]), dtype=_BF16, device=dev)
-            colsum(d["demb"], d["DI"], out=d["dbt"])  # fp32 source: analytically-zero sums stay at fp32 noise
+            if d["demb_colsum"] is not None:
+                d["dbt"] = d["demb_colsum"]  # already reduced (fp32) by the kernel that produced demb
+            else:
+                colsum(d["demb"], d["DI"], out=d["dbt"])  # fp32 source: analytically-zero sums stay at fp32 noise
         # dX = demb Wt (+ fp32 column sums = bias gradient of the second MLP layer)
         gemm_batched([dict(A=d["demb16"], B=d["wt_16"], M=d["B"], N=d["KT"], K=d["DI"], b_mn=True, out16=d["dX16"],
                            colsum=d["dXsum"]) for d in tw])
@@ -918,11 +955,12 @@ class TowerSetFunction(torch.autograd.Function):
             else:
                 parts = [d["dWt_p"][:, :D], d["dWt_p"][:, D8:D8 + D]] + ([d["dWt_p"][:, 2 * D8:2 * D8 + E]] if E else [])
                 dWt = torch.cat(parts, dim=1)
+            pre = d.pop("dtable", None)  # zero-filled on the side stream during forward (first backward only)
             if d["row_exchange"] is not None:
                 ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :D8].contiguous())
-                dtable = scatter_add_rows(rows_all, ids_all, D, d["table_rows"], col_offset=0)
+                dtable = scatter_add_rows(rows_all, ids_all, D, d["table_rows"], col_offset=0, grad=pre)
             else:
-                dtable = scatter_add_rows(d["dX16"], d["ids"], D, d["table_rows"], col_offset=0)
+                dtable = scatter_add_rows(d["dX16"], d["ids"], D, d["table_rows"], col_offset=0, grad=pre)
             dfeats = None
             if d["need_dfeats"]:
                 dfeats = torch.empty((d["B"], d["F"]), dtype=torch.float32, device=dev)
