@@ -271,9 +271,10 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float2 cc2 = scol[c * 32 + i];
-              v[i] = cc2.x * ex2f(fmaf(v[i], LOG2E, -cc2.y));
+            for (int i = 0; i < 32; i += 2) {  // (g, lse) of two columns per 16-byte broadcast load
+              const float4 cc4 = *reinterpret_cast<const float4*>(&scol[c * 32 + i]);
+              v[i] = cc4.x * ex2f(fmaf(v[i], LOG2E, -cc4.y));
+              v[i + 1] = cc4.z * ex2f(fmaf(v[i + 1], LOG2E, -cc4.w));
             }
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
