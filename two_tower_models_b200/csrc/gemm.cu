@@ -4,8 +4,8 @@
 // gradients without materialising a transpose); likewise B is [N,K] or stored [K,N].  bf16 in, fp32
 // accumulate in TMEM, fp32 and/or bf16 out.  One CTA per SM:
 //   warp 0  TMA producer (one lane)     warp 1  UMMA issuer (one lane)     warp 2  TMEM allocator
-//   warps 4-7  epilogue (TMEM -> registers -> global), overlapped with the next tile's main loop through
-//   two TMEM accumulator stages.
+//   warps 4-11 epilogue (TMEM -> registers -> global; two groups of 4 warps, each draining one column half of
+//   the tile), overlapped with the next tile's main loop through two TMEM accumulator stages.
 // Used by the tower MLPs (reference src/two_tower_base_retrieval.py:76-80,90-93,101-110), their
 // backward (autograd of the same) and the history encoder's in/out projections
 // (src/user_history_encoder.py:60-67).
@@ -61,7 +61,7 @@ struct GemmCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ GemmBatch bt) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -87,7 +87,7 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -178,7 +178,8 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter owned by this warp
+    const int q = warp & 3;         // TMEM lane quarter owned by this warp
+    const int e = (warp - 4) >> 2;  // epilogue group: column half of every tile (8 warps drain one accumulator)
     int as = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -192,7 +193,8 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
       const long long row = (long long)m_tile * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = e * (BN / 64) + cc;
         const int n0 = n_tile * BN + c * 32;
         if (n0 >= g.N) break;
         float v[32];
@@ -331,7 +333,7 @@ static int launch_gemm(const GemmBatch& bt, cudaStream_t stream) {
   const int total = bt.work_start[bt.n];
   const int grid = total < num_sms() ? total : num_sms();
   KernelSpan span(bt.g[0].atomic32 ? "gemm_splitk" : "gemm", stream);
-  gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(bt);
+  gemm_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(bt);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -90,7 +90,7 @@ struct ScreenCfg {
 // the largest threshold t with count(score >= t) >= kp, keeps those keys (>= kp of them; more only on exact
 // score ties), returns the new count and threshold.  Warp-cooperative; falls back to an exact sort when ties
 // would leave the list too full.
-__device__ void warp_compact(unsigned long long* list, int n, int kp, unsigned long long* sscr, int lane,
+__device__ void warp_compact(unsigned long long* list, int n, int kp, float tau_in, unsigned long long* sscr, int lane,
                              int& n_out, float& tau_out) {
   unsigned long long k[LCAP / 32];
 #pragma unroll
@@ -103,7 +103,9 @@ __device__ void warp_compact(unsigned long long* list, int n, int kp, unsigned l
   for (int i = 0; i < LCAP / 32; ++i) mx = max(mx, (uint32_t)(k[i] >> 32));
   mx = __reduce_max_sync(0xffffffffu, mx);
   // invariant: count(score >= lo) >= kp, count(score >= hi) < kp
-  uint32_t lo = 1u, hi = mx + 1u;
+  // every key of the list scores >= tau_in (the threshold it was collected under), so the search can start there
+  uint32_t lo = (n >= kp && tau_in > -INFINITY) ? f2ord(tau_in) : 1u, hi = mx + 1u;
+  if (lo >= hi) lo = 1u;
   int clo = n;
   if (mx == 0xffffffffu) hi = mx;  // NaN-ish garbage; keep it bounded
   while (hi - lo > 1u && clo > kp + 32) {
@@ -264,6 +266,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     float* fscr = reinterpret_cast<float*>(sscr);
     // this warp's 32 lists: [cta][e][row][LCAP]
     unsigned long long* wlists = a.lists + (((size_t)blockIdx.x * 2 + e) * QT + q * 32) * LCAP;
+    const int trig = (a.kp + 160 < LCAP - 64) ? a.kp + 160 : LCAP - 64;  // list length that triggers a threshold refresh
     uint32_t t = 0;
     for (int u = 0; u < n_units; ++u) {
       int qb, j0, j1, slot;
@@ -292,28 +295,47 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           uint32_t hits = __ballot_sync(0xffffffffu, m > tau);
           if (hits == 0) continue;
-          const int col0 = j * CN + c * 32;
-          while (hits) {
-            const int r = __ffs(hits) - 1;
-            hits &= hits - 1;
-            if (lane == r) {
+          // Slow path (some row of this warp has a candidate in this chunk).  Every hitting lane parks its 32
+          // scores in its own 128-byte row of the warp scratch (16-byte pieces XOR-swizzled by lane so that a
+          // few simultaneous rows do not collide on banks); then the warp filters the parked rows two at a
+          // time, lane l examining element l of each row - the two rows' load/ballot chains are independent
+          // and overlap.
+          if (m > tau) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(fscr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            __syncwarp();
-            const float x = fscr[lane];
-            const float tau_r = __shfl_sync(0xffffffffu, tau, r);
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(fscr + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          __syncwarp();
+          const int col = j * CN + c * 32 + lane;
+          const bool col_ok = col < a.nc;
+          const uint32_t below = (1u << lane) - 1u;
+          while (hits) {
+            const int r0 = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int r1 = hits ? __ffs(hits) - 1 : r0;
+            const bool two = r1 != r0;
+            if (two) hits &= hits - 1;
+            const float x0 = fscr[r0 * 32 + ((((lane >> 2) ^ (r0 & 7)) << 2) | (lane & 3))];
+            const float x1 = fscr[r1 * 32 + ((((lane >> 2) ^ (r1 & 7)) << 2) | (lane & 3))];
+            const float t0 = __shfl_sync(0xffffffffu, tau, r0), t1 = __shfl_sync(0xffffffffu, tau, r1);
+            const int c0 = __shfl_sync(0xffffffffu, cnt, r0), c1 = __shfl_sync(0xffffffffu, cnt, r1);
+            const bool p0 = (x0 > t0) && col_ok, p1 = two && (x1 > t1) && col_ok;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+            if (p0) wlists[(size_t)r0 * LCAP + c0 + __popc(b0 & below)] = make_key(x0, (uint32_t)col);
+            if (p1) wlists[(size_t)r1 * LCAP + c1 + __popc(b1 & below)] = make_key(x1, (uint32_t)col);
+            if (lane == r0) cnt = c0 + __popc(b0);
+            if (two && lane == r1) cnt = c1 + __popc(b1);
+          }
+          __syncwarp();
+          // lists close to their capacity are cut back to their best entries (threshold refresh); rare
+          uint32_t full = __ballot_sync(0xffffffffu, cnt >= trig);
+          while (full) {
+            const int r = __ffs(full) - 1;
+            full &= full - 1;
             int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
-            const int col = col0 + lane;
-            const bool pass = (x > tau_r) && (col < a.nc);
-            const uint32_t b = __ballot_sync(0xffffffffu, pass);
-            unsigned long long* list = wlists + (size_t)r * LCAP;
-            if (pass) list[cnt_r + __popc(b & ((1u << lane) - 1u))] = make_key(x, (uint32_t)col);
-            cnt_r += __popc(b);
-            float new_tau = tau_r;
-            __syncwarp();
-            if (cnt_r > LCAP - 32) warp_compact(list, cnt_r, a.kp, sscr, lane, cnt_r, new_tau);
+            float new_tau = __shfl_sync(0xffffffffu, tau, r);
+            warp_compact(wlists + (size_t)r * LCAP, cnt_r, a.kp, new_tau, sscr, lane, cnt_r, new_tau);
             if (lane == r) { cnt = cnt_r; tau = new_tau; }
           }
         }
