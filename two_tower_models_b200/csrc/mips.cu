@@ -32,6 +32,7 @@ constexpr int LCAP = 512;   // candidate-list capacity per query row (keys)
 constexpr int KP_MAX = 256; // screening depth limit (k + margin)
 constexpr int QT = 128;     // query rows per tile
 constexpr int CN = 256;     // corpus rows per tile (UMMA N)
+constexpr int QCAP = 32;    // parked rows per warp queue (32 x 128 B = the warp's 4 KB scratch; tags live beside it)
 
 // ---- packed keys: (order-preserving score bits << 32) | ~index ; larger key = better candidate ----------
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -83,7 +84,9 @@ struct ScreenCfg {
   static constexpr int C_BYTES = CN * DP * 2;   // one corpus stage
   static constexpr int STAGES = DP == 64 ? 4 : 2;
   static constexpr int SORT_BYTES = 8 * LCAP * 8;  // one 4 KB scratch per epilogue warp
-  static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * C_BYTES + SORT_BYTES + 1024 + 256;
+  static constexpr int TAG_BYTES = 8 * QCAP * 4;   // (chunk, row) tag per parked row and epilogue warp
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * C_BYTES + SORT_BYTES + TAG_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // Cut the list of `row` (n keys in `list`) back to its best entries: finds by bisection on the score bits
@@ -130,15 +133,15 @@ __device__ void warp_compact(unsigned long long* list, int n, int kp, float tau_
     tau_out = ord2f(lo);
     return;
   }
-  // heavy ties: exact (score, index) order
+  // heavy ties (rare): exact (score, index) order, sorted in place in the list's own (global, L2-resident) storage -
+  // the warp's shared-memory scratch may hold parked rows at this point and must not be touched
+  (void)sscr;
 #pragma unroll
-  for (int i = 0; i < LCAP / 32; ++i) sscr[i * 32 + lane] = k[i];
+  for (int i = 0; i < LCAP / 32; ++i) list[i * 32 + lane] = k[i];
   __syncwarp();
-  warp_sort_desc(sscr, LCAP, lane);
-  for (int e = lane; e < kp; e += 32) list[e] = sscr[e];
-  __syncwarp();
+  warp_sort_desc(list, LCAP, lane);
   n_out = kp;
-  tau_out = ord2f((uint32_t)(sscr[kp - 1] >> 32));
+  tau_out = ord2f((uint32_t)(list[kp - 1] >> 32));
   __syncwarp();
 }
 
@@ -151,7 +154,8 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   uint8_t* sq = smem;                                   // 2 query tiles
   uint8_t* sc = smem + 2 * Cfg::Q_BYTES;                // corpus ring
   unsigned long long* ssort = reinterpret_cast<unsigned long long*>(sc + Cfg::STAGES * Cfg::C_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES);
+  int* stags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES + Cfg::TAG_BYTES);
   uint64_t* q_full = bars;          // [1]
   uint64_t* q_empty = bars + 1;     // [1]
   uint64_t* d_full = bars + 2;      // [2]
@@ -263,7 +267,9 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     const int q = warp & 3;         // TMEM lane quarter
     const int row = q * 32 + lane;  // row of the query tile owned by this thread
     unsigned long long* sscr = ssort + (warp - 4) * LCAP;
-    float* fscr = reinterpret_cast<float*>(sscr);
+    float* fscr = reinterpret_cast<float*>(sscr);                 // parked rows: QCAP x 32 floats
+    int* qmeta = stags + (warp - 4) * QCAP;                       // (chunk << 5) | row tag per parked row
+    unsigned long long* sscr2 = sscr;  // exact-sort fallback of warp_compact: only entered with an empty queue (see drain)
     // this warp's 32 lists: [cta][e][row][LCAP]
     unsigned long long* wlists = a.lists + (((size_t)blockIdx.x * 2 + e) * QT + q * 32) * LCAP;
     const int trig = (a.kp + 160 < LCAP - 64) ? a.kp + 160 : LCAP - 64;  // list length that triggers a threshold refresh
@@ -276,12 +282,52 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       for (int j = j0; j < j1; ++j, ++t) {
         mbar_wait(&d_full[e], t & 1);
         tc_fence_after();
+        // Pass 1 (holds the accumulator): per 32-column chunk a max tree and one compare per row; rows with a
+        // candidate are PARKED (their 32 scores + (row, chunk) tag) in the warp's shared-memory queue.
+        // Pass 2 (after the accumulator has been handed back, i.e. off the UMMA critical path): the parked rows
+        // are filtered against their thresholds and appended to the candidate lists.
+        int nq_ = 0;  // parked rows in the queue (warp-uniform)
+        auto drain = [&]() {
+          const uint32_t below = (1u << lane) - 1u;
+          for (int s0 = 0; s0 < nq_; s0 += 2) {  // two rows per step: their load / ballot chains overlap
+            const int s1 = s0 + 1 < nq_ ? s0 + 1 : s0;
+            const bool two = s1 != s0;
+            const int tag0 = qmeta[s0], tag1 = qmeta[s1];
+            const int r0 = tag0 & 31, r1 = tag1 & 31;
+            const float x0 = fscr[s0 * 32 + lane], x1 = fscr[s1 * 32 + lane];
+            const float t0 = __shfl_sync(0xffffffffu, tau, r0), t1 = __shfl_sync(0xffffffffu, tau, r1);
+            const int c0 = __shfl_sync(0xffffffffu, cnt, r0);
+            const int col0 = j * CN + (tag0 >> 5) * 32 + lane, col1 = j * CN + (tag1 >> 5) * 32 + lane;
+            const bool p0 = (x0 > t0) && (col0 < a.nc);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, p0);
+            if (p0) wlists[(size_t)r0 * LCAP + c0 + __popc(b0 & below)] = make_key(x0, (uint32_t)col0);
+            if (lane == r0) cnt = c0 + __popc(b0);
+            // the second row may be the same query row (another chunk of it): read its count after the update
+            const int c1 = __shfl_sync(0xffffffffu, cnt, r1);
+            const bool p1 = two && (x1 > t1) && (col1 < a.nc);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, p1);
+            if (p1) wlists[(size_t)r1 * LCAP + c1 + __popc(b1 & below)] = make_key(x1, (uint32_t)col1);
+            if (two && lane == r1) cnt = c1 + __popc(b1);
+            // lists close to their capacity are cut back to their best entries (threshold refresh); rare
+            uint32_t full = __ballot_sync(0xffffffffu, cnt >= trig);
+            while (full) {
+              const int r = __ffs(full) - 1;
+              full &= full - 1;
+              int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
+              float new_tau = __shfl_sync(0xffffffffu, tau, r);
+              warp_compact(wlists + (size_t)r * LCAP, cnt_r, a.kp, new_tau, sscr2, lane, cnt_r, new_tau);
+              if (lane == r) { cnt = cnt_r; tau = new_tau; }
+            }
+          }
+          __syncwarp();
+          nq_ = 0;
+        };
 #pragma unroll 1
         for (int c = 0; c < CN / 32; ++c) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * CN + c * 32, v);
           tmem_wait_ld();
-          if (c == CN / 32 - 1) {  // accumulator fully read: hand it back before the last chunk is examined
+          if (c == CN / 32 - 1) {  // accumulator fully read: hand it back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[e]);
@@ -293,52 +339,22 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
           }
           const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          uint32_t hits = __ballot_sync(0xffffffffu, m > tau);
+          const bool hit = m > tau;
+          const uint32_t hits = __ballot_sync(0xffffffffu, hit);
           if (hits == 0) continue;
-          // Slow path (some row of this warp has a candidate in this chunk).  Every hitting lane parks its 32
-          // scores in its own 128-byte row of the warp scratch (16-byte pieces XOR-swizzled by lane so that a
-          // few simultaneous rows do not collide on banks); then the warp filters the parked rows two at a
-          // time, lane l examining element l of each row - the two rows' load/ballot chains are independent
-          // and overlap.
-          if (m > tau) {
+          const int nh = __popc(hits);
+          if (nq_ + nh > QCAP) drain();  // queue full (early in a scan): filter what is parked first
+          if (hit) {
+            const int s_ = nq_ + __popc(hits & ((1u << lane) - 1u));
+            qmeta[s_] = (c << 5) | lane;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(fscr + lane * 32 + ((i ^ (lane & 7)) << 2)) =
-                  make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              *reinterpret_cast<float4*>(fscr + s_ * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
+          nq_ += nh;
           __syncwarp();
-          const int col = j * CN + c * 32 + lane;
-          const bool col_ok = col < a.nc;
-          const uint32_t below = (1u << lane) - 1u;
-          while (hits) {
-            const int r0 = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const int r1 = hits ? __ffs(hits) - 1 : r0;
-            const bool two = r1 != r0;
-            if (two) hits &= hits - 1;
-            const float x0 = fscr[r0 * 32 + ((((lane >> 2) ^ (r0 & 7)) << 2) | (lane & 3))];
-            const float x1 = fscr[r1 * 32 + ((((lane >> 2) ^ (r1 & 7)) << 2) | (lane & 3))];
-            const float t0 = __shfl_sync(0xffffffffu, tau, r0), t1 = __shfl_sync(0xffffffffu, tau, r1);
-            const int c0 = __shfl_sync(0xffffffffu, cnt, r0), c1 = __shfl_sync(0xffffffffu, cnt, r1);
-            const bool p0 = (x0 > t0) && col_ok, p1 = two && (x1 > t1) && col_ok;
-            const uint32_t b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-            if (p0) wlists[(size_t)r0 * LCAP + c0 + __popc(b0 & below)] = make_key(x0, (uint32_t)col);
-            if (p1) wlists[(size_t)r1 * LCAP + c1 + __popc(b1 & below)] = make_key(x1, (uint32_t)col);
-            if (lane == r0) cnt = c0 + __popc(b0);
-            if (two && lane == r1) cnt = c1 + __popc(b1);
-          }
-          __syncwarp();
-          // lists close to their capacity are cut back to their best entries (threshold refresh); rare
-          uint32_t full = __ballot_sync(0xffffffffu, cnt >= trig);
-          while (full) {
-            const int r = __ffs(full) - 1;
-            full &= full - 1;
-            int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
-            float new_tau = __shfl_sync(0xffffffffu, tau, r);
-            warp_compact(wlists + (size_t)r * LCAP, cnt_r, a.kp, new_tau, sscr, lane, cnt_r, new_tau);
-            if (lane == r) { cnt = cnt_r; tau = new_tau; }
-          }
         }
+        if (nq_ > 0) drain();
       }
       // unit done: exact order of each row's list, best kp keys -> part[slot][e][row][kp]
       for (int r = 0; r < 32; ++r) {
