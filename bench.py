@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--features", type=int, default=128)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-ce", action="store_true",
+                    help="N > 1: scoring kernels read the item shards from peer memory (no NCCL all-gather)")
     ap.add_argument("--workload", default="base", choices=["base", "history", "mips"],
                     help="base = BASELINE configs[1] (the driver's bench line); history = configs[2]; mips = configs[3]")
     ap.add_argument("--queries", type=int, default=65536)
@@ -165,7 +167,8 @@ def workload_config(args, world):
         "workload": f"TwoTowerBaseRetrieval.train_forward+backward d={args.d} F={args.features} batch={args.batch}/GPU "
                     f"hash={HASH} T=1 (BASELINE configs[1])",
         "global_batch": args.batch * world, "d": args.d, "parallelism": f"dp{world}" if world > 1 else "single",
-        "negatives": "in-batch, all-gathered over NCCL" if world > 1 else "in-batch",
+        "negatives": ("in-batch, read in place from peer memory over NVLink" if getattr(args, "peer_ce", False)
+                      else "in-batch, all-gathered over NCCL") if world > 1 else "in-batch",
         "l2": f"input ring of {RING} batches > 126 MB L2",
         "step": "train_forward + loss.backward(), gradients of all 14 parameter tensors, weights re-cast to bf16 every step",
     }
@@ -401,7 +404,7 @@ def main():
     if world > 1:
         from two_tower_models_b200 import distributed as ttd
 
-        ttd.enable_data_parallel(model)
+        ttd.enable_data_parallel(model, peer_memory=True if args.peer_ce else None)
 
     gen = torch.Generator().manual_seed(1 + rank)
     host_ring = [{k: v.pin_memory() for k, v in make_batch(B, F, gen).items()} for _ in range(RING)]

@@ -162,6 +162,20 @@ int tt_mips_topk(const void* Q_bf16, int64_t ldq16, const void* C_bf16, int64_t 
                  int64_t ldq32, const float* C_f32, int64_t ldc32, int64_t nq, int64_t nc, int64_t d, int64_t k,
                  int64_t* idx, float* scores, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same two entry points with the item matrix V given as n_parts equally sized row blocks
+ * V = [V_parts[0]; V_parts[1]; ...] (rows_per_part rows each, a multiple of 128; n_parts <= 8).  The blocks may live in
+ * the memory of peer GPUs (mapped through CUDA IPC / symmetric memory): the kernels read them in place over NVLink
+ * with TMA, so the data-parallel loss needs no all-gather of the item embeddings.  V_parts is a HOST array of
+ * device pointers. */
+int tt_inbatch_ce_fwd_parts(const void* U_bf16, int64_t ldu, const void* const* V_parts_host, int32_t n_parts,
+                            int64_t rows_per_part, int64_t ldv, int64_t B, int64_t N, int64_t d, int64_t target_offset,
+                            float* ce, float* lse, void* workspace, int64_t workspace_bytes, void* stream);
+int tt_inbatch_ce_bwd_parts(const void* U_bf16, int64_t ldu, const void* const* V_parts_host, int32_t n_parts,
+                            int64_t rows_per_part, int64_t ldv, int64_t B, int64_t N, int64_t d, int64_t target_offset,
+                            const float* lse, const float* g, float* dU_f32, int64_t lddu, void* dU_bf16, int64_t lddu16,
+                            float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
+                            float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- history encoder helpers ---------------------------------------------------------------- */
 
 /* x_bf16[b*H+h, :] = bf16(table[ids[b,h]] + pe[h]) (pe may be NULL);  mean[b, :] = mean_h table[ids[b,h]].

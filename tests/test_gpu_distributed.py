@@ -37,7 +37,7 @@ def _problem():
 ORDER = ["user_id", "user_features", "user_history", "item_id", "item_features", "position", "labels"]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, peer):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -48,7 +48,7 @@ def _worker(rank, world, port, out):
         n = batch["user_id"].shape[0] // world
         loc = {k: v[rank * n:(rank + 1) * n].cuda() for k, v in batch.items()}
         m = _build(p, uvw).cuda()
-        ctx = ttd.enable_data_parallel(m)
+        ctx = ttd.enable_data_parallel(m, peer_memory=peer)
         loss = m.train_forward(*[loc[k] for k in ORDER])
         loss.backward()
         ctx.sync_gradients(m)
@@ -60,7 +60,8 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_step_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl_allgather", "peer_memory"])
+def test_two_gpu_sharded_step_matches_single_gpu(tmp_path, peer):
     from helpers import assert_close_fro
 
     s = socket.socket()
@@ -68,7 +69,7 @@ def test_two_gpu_sharded_step_matches_single_gpu(tmp_path):
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, peer), nprocs=2, join=True)
     got = torch.load(out)
     p, uvw, batch = _problem()
     m = _build(p, uvw).cuda()

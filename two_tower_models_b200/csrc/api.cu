@@ -225,6 +225,22 @@ int tt_inbatch_ce_bwd(const void* U, int64_t ldu, const void* V, int64_t ldv, in
                         dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream));
 }
 
+int tt_inbatch_ce_fwd_parts(const void* U, int64_t ldu, const void* const* Vp, int32_t np, int64_t rows_per_part, int64_t ldv,
+                            int64_t B, int64_t N, int64_t d, int64_t target_offset, float* ce, float* lse, void* ws,
+                            int64_t ws_bytes, void* stream) {
+  TT_CHECK(Vp != nullptr, "tt_inbatch_ce_fwd_parts: null part list");
+  return inbatch_ce_fwd_parts(U, ldu, Vp, np, rows_per_part, ldv, B, N, d, target_offset, ce, lse, ws, (size_t)ws_bytes,
+                              S(stream));
+}
+int tt_inbatch_ce_bwd_parts(const void* U, int64_t ldu, const void* const* Vp, int32_t np, int64_t rows_per_part, int64_t ldv,
+                            int64_t B, int64_t N, int64_t d, int64_t target_offset, const float* lse, const float* g,
+                            float* dU, int64_t lddu, void* dU16, int64_t lddu16, float* dV, int64_t lddv, void* dV16,
+                            int64_t lddv16, float* dU_colsum, float* dV_colsum, void* ws, int64_t ws_bytes, void* stream) {
+  TT_CHECK(Vp != nullptr, "tt_inbatch_ce_bwd_parts: null part list");
+  return inbatch_ce_bwd_parts(U, ldu, Vp, np, rows_per_part, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV,
+                              lddv, dV16, lddv16, dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream));
+}
+
 int tt_weighted_loss(const float* ce, const float* labels, int64_t ldl, const float* weights, int64_t B, int64_t T,
                      float* loss, float* g, void* stream) {
   return weighted_loss(ce, labels, ldl, weights, B, T, loss, g, S(stream));

@@ -57,7 +57,7 @@ struct CeFwdCfg {
 // kernel merges the (slot, group) partials.
 template <int DP>
 __global__ void __launch_bounds__(384, 1)
-ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeFwdArgs a) {
+ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TmapSet tmy, const CeFwdArgs a) {
   using Cfg = CeFwdCfg<DP>;
   constexpr int BN = Cfg::BN, NS = Cfg::NS;
   extern __shared__ uint8_t smem_raw[];
@@ -76,7 +76,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
-    tma_prefetch_desc(&tmy);
+    for (int p = 0; p < tmy.n; ++p) tma_prefetch_desc(&tmy.m[p]);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
@@ -111,8 +111,10 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
           mbar_wait(&y_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&y_full[stage], Cfg::Y_BYTES);
           uint8_t* dst = sy + stage * Cfg::Y_BYTES;
+          int yrow;
+          const CUtensorMap* my = tmap_of(tmy, j * BN, yrow);
 #pragma unroll
-          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), &tmy, &y_full[stage], b * 64, j * BN);
+          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), my, &y_full[stage], b * 64, yrow);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         ++xs;
@@ -256,6 +258,23 @@ __global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, co
 
 static int pick_dp(long long d) { return d <= 64 ? 64 : (d <= 128 ? 128 : 256); }
 
+// Tensor maps of an [rows, d] operand given as `np` equally sized row blocks (np == 1: one matrix)
+static int make_tmap_set(TmapSet* t, const void* const* parts, int np, long long rows_per_part, long long rows,
+                         long long d, long long ld, int box_rows) {
+  TT_CHECK(np >= 1 && np <= 8, "in-batch CE: 1..8 operand parts supported (got %d)", np);
+  TT_CHECK(np == 1 || (rows_per_part % 128 == 0 && rows_per_part * np == rows),
+           "in-batch CE: operand parts must be equally sized multiples of 128 rows (%lld x %d != %lld)", rows_per_part, np, rows);
+  t->n = np;
+  t->rows_per_map = (int)(np == 1 ? rows : rows_per_part);
+  for (int p = 0; p < np; ++p) {
+    TT_CHECK(((uintptr_t)parts[p] % 16) == 0, "in-batch CE: operand parts need 16-byte alignment");
+    const int rc = make_tmap_bf16(&t->m[p], parts[p], d, np == 1 ? rows : rows_per_part, ld, 64, box_rows);
+    if (rc) return rc;
+  }
+  for (int p = np; p < 8; ++p) t->m[p] = t->m[0];
+  return 0;
+}
+
 static size_t fwd_ws_bytes(const Sched& s, long long Bpad) {
   return (size_t)(2 * (size_t)s.max_slots * 2 * Bpad + Bpad) * sizeof(float);
 }
@@ -273,7 +292,7 @@ size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d) {
 }
 
 template <int DP>
-static int launch_ce_fwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeFwdArgs& a, int grid, cudaStream_t st) {
+static int launch_ce_fwd(const CUtensorMap& tx, const TmapSet& ty, const CeFwdArgs& a, int grid, cudaStream_t st) {
   using Cfg = CeFwdCfg<DP>;
   static bool configured = false;
   if (!configured) {
@@ -289,6 +308,13 @@ static int launch_ce_fwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeF
 
 int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, float* ce, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return inbatch_ce_fwd_parts(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, ws, ws_bytes, stream);
+}
+
+int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                         long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
+                         float* lse, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const void* V = Vp[0];
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_fwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_fwd: embedding dim %lld > 256 is not supported", d);
   TT_CHECK(target_offset >= 0 && target_offset + B <= N, "inbatch_ce_fwd: targets [%lld, %lld) outside the %lld item columns",
@@ -307,10 +333,11 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
   a.diag = a.part_s + (size_t)s.max_slots * 2 * Bpad;
   a.trace = nullptr;
   if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
-  CUtensorMap tx, ty;
+  CUtensorMap tx;
+  TmapSet ty;
   int rc = make_tmap_bf16(&tx, U, d, B, ldu, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&ty, V, d, N, ldv, 64, 128);
+  rc = make_tmap_set(&ty, Vp, np, rows_per_part, N, d, ldv, 128);
   if (rc) return rc;
   if (DP == 64) rc = launch_ce_fwd<64>(tx, ty, a, s.grid, stream);
   else if (DP == 128) rc = launch_ce_fwd<128>(tx, ty, a, s.grid, stream);
@@ -324,317 +351,8 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
 }
 
 // =============================================================================================
-// Backward (generic two-UMMA kernel)
+// Backward: host side (the kernel is ce_bwd2.cu)
 // =============================================================================================
-template <int DP>
-struct CeBwdCfg {
-  static constexpr int BN = DP == 256 ? 64 : 128;
-  static constexpr int NS = DP == 256 ? 4 : 3;  // score-tile buffers in TMEM
-  static constexpr int LOOKAHEAD = NS - 1;      // S = X Y^T runs at most this many tiles ahead of acc += E Y
-  static constexpr int KBOX = DP / 64;
-  static constexpr int X_BYTES = 128 * DP * 2;
-  static constexpr int Y_BYTES = BN * DP * 2;
-  static constexpr int P_BYTES = 128 * BN * 2;  // ONE E tile; its two column halves are handed over separately
-  // tile t's Y is live from S(t) until acc += E(t) Y(t) (~ one epilogue + TMA latency): a deep ring keeps the
-  // loads ahead of the UMMA warp
-  static constexpr int STAGES = DP == 64 ? 8 : (DP == 128 ? 5 : 4);
-  static constexpr int COLSTAT_BYTES = BN * 8;  // [BN] float2
-  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + P_BYTES + COLSTAT_BYTES + 1024 + 256;
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static constexpr int ACC_COL = NS * BN;
-  static_assert(ACC_COL + DP <= 512, "TMEM budget");
-};
-
-// Both epilogue groups work on every score tile (group e: columns [BN/2 e, BN/2 (e+1))): the tile that is
-// ready keeps all 8 epilogue warps busy while the UMMA warp already produces the next score tiles.
-template <int DP, bool COLSTATS>
-__global__ void __launch_bounds__(384, 1)
-ce_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeBwdArgs a) {
-  using Cfg = CeBwdCfg<DP>;
-  constexpr int BN = Cfg::BN, NS = Cfg::NS;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sx = smem;
-  uint8_t* sy = sx + Cfg::X_BYTES;
-  uint8_t* sp = sy + Cfg::STAGES * Cfg::Y_BYTES;
-  float2* scol = reinterpret_cast<float2*>(sp + Cfg::P_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scol) + Cfg::COLSTAT_BYTES);
-  uint64_t* x_full = bars;
-  uint64_t* x_empty = bars + 1;
-  uint64_t* acc_full = bars + 2;
-  uint64_t* acc_empty = bars + 3;
-  uint64_t* p_full = bars + 4;   // [2]
-  uint64_t* p_empty = bars + 6;  // [2]
-  uint64_t* s_full = bars + 8;   // [NS]
-  uint64_t* s_empty = s_full + NS;
-  uint64_t* y_full = s_empty + NS;
-  uint64_t* y_empty = y_full + Cfg::STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // trace layout: [role 0..3][tile 0..63][2]; role 0 = UMMA-1 issue, 1 = UMMA-2 issue, 2/3 = epilogue group 0/1
-#define CE_STAMP(role, tile, which)                                                           \
-  do {                                                                                        \
-    if (a.trace != nullptr && blockIdx.x == 0 && (tile) < 64) a.trace[((role) * 64 + (tile)) * 2 + (which)] = clock64(); \
-  } while (0)
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmx);
-    tma_prefetch_desc(&tmy);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1);
-    mbar_init(x_empty, 1);
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);
-    for (int i = 0; i < 2; ++i) {  // per column half of the E tile
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_empty[i], 1);
-    }
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
-    }
-    for (int i = 0; i < Cfg::STAGES; ++i) {
-      mbar_init(&y_full[i], 1);
-      mbar_init(&y_empty[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_holder, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      SegIter it(a.T, a.total, a.CT);
-      int r, j0, j1, stage = 0;
-      uint32_t phase = 0, xs = 0;
-      while (it.next(r, j0, j1)) {
-        mbar_wait(x_empty, (xs & 1) ^ 1);
-        mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
-#pragma unroll
-        for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(sx + b * 16384, &tmx, x_full, b * 64, r * 128);
-        for (int j = j0; j < j1; ++j) {
-          mbar_wait(&y_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&y_full[stage], Cfg::Y_BYTES);
-          uint8_t* dst = sy + stage * Cfg::Y_BYTES;
-#pragma unroll
-          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), &tmy, &y_full[stage], b * 64, j * BN);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-        ++xs;
-      }
-    }
-  } else if (warp == 1) {
-    {  // the whole warp walks the schedule; only the elected lane issues tcgen05 instructions
-      const uint32_t leader = elect_one();
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);  // S = X Y^T
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, DP, 0, 1);  // acc += E Y   (Y read MN-major)
-      SegIter it(a.T, a.total, a.CT);
-      int r, j0, j1;
-      int stage1 = 0, stage2 = 0;  // Y ring positions of the next UMMA-1 / UMMA-2
-      uint32_t phase1 = 0;
-      uint32_t t1 = 0, t2 = 0, xs = 0;
-      const uint64_t dx0 = make_smem_desc_sw128(smem_u32(sx), 0, 1024);          // X, K-major
-      const uint64_t dy0 = make_smem_desc_sw128(smem_u32(sy), 0, 1024);          // Y, K-major  (S = X Y^T)
-      const uint64_t dyt0 = make_smem_desc_sw128(smem_u32(sy), BN * 128, 1024);  // Y, MN-major (acc += E Y)
-      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sp), 0, 1024);          // E, K-major
-      auto mma1 = [&]() {
-        const uint32_t buf = t1 % NS, use = t1 / NS;
-        mbar_wait(&y_full[stage1], phase1);
-        if (leader) CE_STAMP(0, t1, 0);
-        mbar_wait(&s_empty[buf], (use & 1) ^ 1);
-        tc_fence_after();
-        if (leader) CE_STAMP(0, t1, 1);
-        const uint64_t dy = desc_advance(dy0, stage1 * Cfg::Y_BYTES);
-#pragma unroll
-        for (int k = 0; k < DP / 16; ++k)
-          umma_bf16_w(tmem_base + buf * BN, desc_advance(dx0, (k >> 2) * 16384 + (k & 3) * 32),
-                      desc_advance(dy, (k >> 2) * (BN * 128) + (k & 3) * 32), idesc1, k > 0 ? 1u : 0u, leader);
-        umma_commit_w(&s_full[buf], leader);
-        if (++stage1 == Cfg::STAGES) { stage1 = 0; phase1 ^= 1; }
-        ++t1;
-      };
-      auto mma2 = [&](bool first) {
-        constexpr int KH = BN / 32;  // K = 16 steps per column half of E
-        const uint64_t dyt = desc_advance(dyt0, stage2 * Cfg::Y_BYTES);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 0 && leader) CE_STAMP(1, t2, 0);
-          mbar_wait(&p_full[h], t2 & 1);
-          tc_fence_after();
-          if (h == 1 && leader) CE_STAMP(1, t2, 1);
-#pragma unroll
-          for (int kk = 0; kk < KH; ++kk) {
-            const int k = h * KH + kk;
-            umma_bf16_w(tmem_base + Cfg::ACC_COL, desc_advance(dp0, (k >> 2) * 16384 + (k & 3) * 32),
-                        desc_advance(dyt, k * 2048), idesc2, (!first || k > 0) ? 1u : 0u, leader);
-          }
-          umma_commit_w(&p_empty[h], leader);
-        }
-        umma_commit_w(&y_empty[stage2], leader);
-        if (++stage2 == Cfg::STAGES) stage2 = 0;
-        ++t2;
-      };
-      while (it.next(r, j0, j1)) {
-        const int n = j1 - j0;
-        int issued = 0;
-        mbar_wait(x_full, xs & 1);
-        for (int i = 0; i < n; ++i) {
-          while (issued < n && issued <= i + Cfg::LOOKAHEAD) {
-            mma1();
-            if (++issued == n) umma_commit_w(x_empty, leader);  // all S = X Y^T of this segment issued
-          }
-          if (i == 0) {
-            mbar_wait(acc_empty, (xs & 1) ^ 1);
-            tc_fence_after();
-          }
-          mma2(i == 0);
-        }
-        umma_commit_w(acc_full, leader);
-        ++xs;
-      }
-    }
-  } else if (warp >= 4) {
-    const int e = (warp - 4) >> 2;  // column half of every tile
-    const int q = warp & 3;
-    const int wg_tid = threadIdx.x - 128 - e * 128;  // 0..127 inside the epilogue group
-    constexpr int CH = BN / 64;                       // 32-column chunks per group and tile
-    SegIter it(a.T, a.total, a.CT);
-    int r, j0, j1;
-    uint32_t t = 0, xs = 0;
-    const uint32_t prow = q * 32 + lane;  // row of the 128-row tile owned by this thread
-    while (it.next(r, j0, j1)) {
-      const long long row = (long long)r * 128 + prow;
-      const bool valid = row < a.XR;
-      float rs = 1.f, rl = 0.f;
-      if (!COLSTATS) {
-        rs = valid ? a.g[row] : 0.f;
-        rl = valid ? a.lse[row] * LOG2E : 0.f;
-      }
-      const long long tgt = row + a.diag_shift;
-      for (int j = j0; j < j1; ++j, ++t) {
-        const uint32_t buf = t % NS;
-        if (COLSTATS) {
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");  // previous tile's readers are done
-          if (wg_tid < BN / 2) {
-            const int cidx = e * (BN / 2) + wg_tid;
-            const long long col = (long long)j * BN + cidx;
-            const bool cv = col < a.YR;
-            scol[cidx] = make_float2(cv ? a.g[col] : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
-        }
-        mbar_wait(&s_full[buf], (t / NS) & 1);
-        tc_fence_after();
-        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 0);
-        // E = g (exp(S - lse) - [positive]) for the 32 columns starting at tile column c*32, in place
-        auto transform = [&](float* v, int c) {
-          const long long n0 = (long long)j * BN + c * 32;
-          if (a.dbg & 4) return;
-          if (!COLSTATS) {
-            if (a.dbg & 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = rs * fmaf(v[i], LOG2E, -rl);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
-            }
-            if (tgt >= n0 && tgt < n0 + 32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n0 + i == tgt) v[i] -= rs;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float2 cc2 = scol[c * 32 + i];
-              v[i] = cc2.x * ex2f(fmaf(v[i], LOG2E, -cc2.y));
-            }
-            if (tgt >= n0 && tgt < n0 + 32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n0 + i == tgt) v[i] -= scol[c * 32 + i].x;
-            }
-          }
-        };
-        // bf16 pack + swizzled store: columns [c*32, c*32+32) of the E tile = 4 x 16-byte chunks
-        auto store = [&](const float* v, int c) {
-          if (a.dbg & 2) return;
-          uint8_t* box = sp + ((c * 32) >> 6) * 16384;
-          const uint32_t chunk0 = ((c * 32) & 63) >> 3;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
-            o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
-            o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
-            o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
-            *reinterpret_cast<uint4*>(box + sw128_offset(prow, chunk0 + h)) = o;
-          }
-        };
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * (CH * 32);
-        float v0[32];
-        tmem_ld32(taddr, v0);
-        tmem_wait_ld();
-        if (CH == 2) {
-          float v1[32];
-          tmem_ld32(taddr + 32, v1);  // in flight while the first chunk is transformed
-          transform(v0, e * CH);
-          mbar_wait(&p_empty[e], (t & 1) ^ 1);  // acc += E(t-1) Y(t-1) has consumed this half of the E tile
-          store(v0, e * CH);
-          tmem_wait_ld();
-          transform(v1, e * CH + 1);
-          store(v1, e * CH + 1);
-        } else {
-          transform(v0, e * CH);
-          mbar_wait(&p_empty[e], (t & 1) ^ 1);
-          store(v0, e * CH);
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[buf]);
-          mbar_arrive(&p_full[e]);
-        }
-        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 1);
-      }
-      // segment accumulator -> partial slot (each group drains half of the columns)
-      mbar_wait(acc_full, xs & 1);
-      tc_fence_after();
-      {
-        const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
-        float* dst = a.partial + (long long)slot * a.slot_stride + row * DP;
-#pragma unroll 1
-        for (int c = 0; c < DP / 64; ++c) {
-          const int col = e * (DP / 2) + c * 32;
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::ACC_COL + col, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(dst + col + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      ++xs;
-    }
-  }
-#undef CE_STAMP
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // out[row, c] = sum over the slots that touched row's tile; one launch handles up to two results (dU and dV) and
 // optionally accumulates the fp32 column sums of each result (= the bias gradient of the tower Linear above it).
 struct ReduceJob {
@@ -686,28 +404,14 @@ ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
   }
 }
 
-template <int DP, bool COLSTATS>
-static int launch_ce_bwd(const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid, cudaStream_t st) {
-  using Cfg = CeBwdCfg<DP>;
-  static bool configured = false;
-  if (!configured) {
-    TT_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<DP, COLSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
-  KernelSpan span(COLSTATS ? "ce_bwd_kernel_dV" : "ce_bwd_kernel_dU", st);
-  ce_bwd_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
-  TT_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 template <int DP>
-static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr, const void* Y, long long ldy,
+static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long x_rows_per_part, long long ldx, long long xr,
+                       const void* const* Yp, int nyp, long long y_rows_per_part, long long ldy,
                        long long yr, long long d, long long diag_shift, const float* g, const float* lse, float* out32,
                        long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
                        ReduceJob& job, cudaStream_t stream) {
-  using Cfg = CeBwdCfg<DP>;
-  const Sched s = make_sched(xr, yr, Cfg::BN);
+  constexpr int BN = DP == 256 ? 64 : 128;
+  const Sched s = make_sched(xr, yr, BN);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
   CeBwdArgs a;
   a.XR = (int)xr; a.YR = (int)yr; a.diag_shift = diag_shift;
@@ -721,14 +425,12 @@ static int ce_bwd_pass(bool colstats, const void* X, long long ldx, long long xr
   if (const char* db = getenv("TT_CE_DBG")) a.dbg = atoi(db);
   a.cta_times = nullptr;
   if (const char* ct = getenv("TT_CE_CTA_TIMES")) a.cta_times = (unsigned long long*)strtoull(ct, nullptr, 0);
-  CUtensorMap tx, ty;
-  int rc = make_tmap_bf16(&tx, X, d, xr, ldx, 64, 128);
+  TmapSet tx, ty;
+  int rc = make_tmap_set(&tx, Xp, nxp, x_rows_per_part, xr, d, ldx, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&ty, Y, d, yr, ldy, 64, Cfg::BN);
+  rc = make_tmap_set(&ty, Yp, nyp, y_rows_per_part, yr, d, ldy, BN);
   if (rc) return rc;
-  static const int version = getenv("TT_CE_BWD") ? atoi(getenv("TT_CE_BWD")) : 2;
-  if (version == 2) rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
-  else rc = colstats ? launch_ce_bwd<DP, true>(tx, ty, a, s.grid, stream) : launch_ce_bwd<DP, false>(tx, ty, a, s.grid, stream);
+  rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
   if (rc) return rc;
   job.rows = (int)xr; job.d = (int)d; job.CT = s.CT; job.T = s.T; job.slot_stride = a.slot_stride;
   job.partial = a.partial; job.out32 = out32; job.ld32 = ld32; job.out16 = (bf16*)out16; job.ld16 = ld16;
@@ -741,6 +443,16 @@ int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, l
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
                    long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, float* dU_colsum,
                    float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return inbatch_ce_bwd_parts(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16,
+                              lddv16, dU_colsum, dV_colsum, ws, ws_bytes, stream);
+}
+
+int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                         long long ldv, long long B, long long N, long long d, long long target_offset, const float* lse,
+                         const float* g, float* dU, long long lddu, void* dU16, long long lddu16, float* dV, long long lddv,
+                         void* dV16, long long lddv16, float* dU_colsum, float* dV_colsum, void* ws, size_t ws_bytes,
+                         cudaStream_t stream) {
+  const void* V = Vp[0];
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_bwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_bwd: embedding dim %lld > 256 is not supported", d);
   TT_CHECK((ldu % 8) == 0 && (ldv % 8) == 0 && ((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0,
@@ -757,11 +469,11 @@ int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, l
 #define TT_PASS(DPV)                                                                                                 \
   do {                                                                                                               \
     if (wantU)                                                                                                       \
-      rc = ce_bwd_pass<DPV>(false, U, ldu, B, V, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, lddu16, dU_colsum, ws, \
-                            offB, ja, stream);                                                                       \
+      rc = ce_bwd_pass<DPV>(false, &U, 1, B, ldu, B, Vp, np, rows_per_part, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, \
+                            lddu16, dU_colsum, ws, offB, ja, stream);                                                \
     if (rc == 0 && wantV)                                                                                            \
-      rc = ce_bwd_pass<DPV>(true, V, ldv, N, U, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, lddv16, dV_colsum,  \
-                            (char*)ws + offB, ws_bytes - offB, jb, stream);                                          \
+      rc = ce_bwd_pass<DPV>(true, Vp, np, rows_per_part, ldv, N, &U, 1, B, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, \
+                            lddv16, dV_colsum, (char*)ws + offB, ws_bytes - offB, jb, stream);                       \
   } while (0)
   if (DP == 64) TT_PASS(64);
   else if (DP == 128) TT_PASS(128);

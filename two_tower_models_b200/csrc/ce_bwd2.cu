@@ -42,7 +42,7 @@ struct Cfg2 {
 
 template <int DP, bool COLSTATS>
 __global__ void __launch_bounds__(384, 1)
-ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const CeBwdArgs a) {
+ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ TmapSet tmy, const CeBwdArgs a) {
   using Cfg = Cfg2<DP>;
   constexpr int BN = Cfg::BN, NS = Cfg::NS;
   constexpr bool XT = Cfg::XT;
@@ -80,8 +80,8 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
     if (a.trace != nullptr && blockIdx.x == 0 && (tile) < 64) a.trace[((role) * 64 + (tile)) * 2 + (which)] = clock64(); \
   } while (0)
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmx);
-    tma_prefetch_desc(&tmy);
+    for (int p = 0; p < tmx.n; ++p) tma_prefetch_desc(&tmx.m[p]);
+    for (int p = 0; p < tmy.n; ++p) tma_prefetch_desc(&tmy.m[p]);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
@@ -118,14 +118,18 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
       while (it.next(r, j0, j1)) {
         mbar_wait(x_empty, (xs & 1) ^ 1);
         mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
+        int xrow;
+        const CUtensorMap* mx = tmap_of(tmx, r * 128, xrow);
 #pragma unroll
-        for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(sx + b * 16384, &tmx, x_full, b * 64, r * 128);
+        for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(sx + b * 16384, mx, x_full, b * 64, xrow);
         for (int j = j0; j < j1; ++j) {
           mbar_wait(&y_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&y_full[stage], Cfg::Y_BYTES);
           uint8_t* dst = sy + stage * Cfg::Y_BYTES;
+          int yrow;
+          const CUtensorMap* my = tmap_of(tmy, j * BN, yrow);
 #pragma unroll
-          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), &tmy, &y_full[stage], b * 64, j * BN);
+          for (int b = 0; b < Cfg::KBOX; ++b) tma_load_2d(dst + b * (BN * 128), my, &y_full[stage], b * 64, yrow);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         ++xs;
@@ -354,7 +358,7 @@ ce_bwd2_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ 
 }
 
 template <int DP, bool COLSTATS>
-int launch2(const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid, cudaStream_t st) {
+int launch2(const TmapSet& tx, const TmapSet& ty, const CeBwdArgs& a, int grid, cudaStream_t st) {
   using Cfg = Cfg2<DP>;
   static bool configured = false;
   if (!configured) {
@@ -370,7 +374,7 @@ int launch2(const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, in
 
 }  // namespace
 
-int launch_ce_bwd2(int DP, bool colstats, const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid,
+int launch_ce_bwd2(int DP, bool colstats, const TmapSet& tx, const TmapSet& ty, const CeBwdArgs& a, int grid,
                    cudaStream_t st) {
   if (DP == 64) return colstats ? launch2<64, true>(tx, ty, a, grid, st) : launch2<64, false>(tx, ty, a, grid, st);
   if (DP == 128) return colstats ? launch2<128, true>(tx, ty, a, grid, st) : launch2<128, false>(tx, ty, a, grid, st);

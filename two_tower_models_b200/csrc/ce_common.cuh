@@ -42,6 +42,20 @@ static inline Sched make_sched(long long x_rows, long long y_rows, int BN) {
   return s;
 }
 
+// An operand whose rows are spread over up to 8 equally sized parts (one tensor map each): the all-gathered item
+// embeddings of the data-parallel loss, read IN PLACE from the peers' memory over NVLink.  n == 1: a plain matrix.
+struct TmapSet {
+  CUtensorMap m[8];
+  int n;
+  int rows_per_map;
+};
+// tensor map + row coordinate of global row `row` (row and rows_per_map are multiples of the box height)
+__device__ __forceinline__ const CUtensorMap* tmap_of(const TmapSet& t, int row, int& local_row) {
+  const int p = t.n == 1 ? 0 : row / t.rows_per_map;
+  local_row = row - p * t.rows_per_map;
+  return &t.m[p];
+}
+
 struct CeBwdArgs {
   int XR, YR;            // valid rows of X / Y
   long long diag_shift;  // element (row, col) is a positive when col == row + diag_shift
@@ -58,7 +72,7 @@ struct CeBwdArgs {
 
 
 // v2 backward kernel (ce_bwd2.cu): E operand and X tile in tensor memory
-int launch_ce_bwd2(int DP, bool colstats, const CUtensorMap& tx, const CUtensorMap& ty, const CeBwdArgs& a, int grid,
+int launch_ce_bwd2(int DP, bool colstats, const TmapSet& tx, const TmapSet& ty, const CeBwdArgs& a, int grid,
                    cudaStream_t st);
 
 }  // namespace tt

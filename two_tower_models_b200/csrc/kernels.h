@@ -34,6 +34,16 @@ int gemm_bf16_batched(const GemmDesc* d, int n, cudaStream_t stream);
 size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d);
 int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, float* ce, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
+// The same with the item matrix V given as `np` equally sized row blocks (e.g. the peers' buffers of a data-parallel
+// step, read in place over NVLink): V = [Vp[0]; Vp[1]; ...], rows_per_part rows each (a multiple of 128).
+int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                         long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
+                         float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
+int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                         long long ldv, long long B, long long N, long long d, long long target_offset, const float* lse,
+                         const float* g, float* dU, long long lddu, void* dU16, long long lddu16, float* dV, long long lddv,
+                         void* dV16, long long lddv16, float* dU_colsum, float* dV_colsum, void* ws, size_t ws_bytes,
+                         cudaStream_t stream);
 // dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,

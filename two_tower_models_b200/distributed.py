@@ -81,8 +81,61 @@ class ShardedInBatchCE(torch.autograd.Function):
         return dU, dV, None, None
 
 
+class _PeerItemBuffers:
+    """One symmetric-memory buffer per rank for the bf16 item embeddings: every rank writes its shard into its own
+    buffer and the scoring kernels of all ranks read all shards IN PLACE over NVLink (TMA loads from the peers'
+    memory), so the all-gather of V disappears into the kernel that consumes it."""
+
+    def __init__(self, group, rows, pitch, device):
+        import torch.distributed._symmetric_memory as symm
+
+        pg = group if group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty((rows, pitch), dtype=torch.bfloat16, device=device)
+        self.hdl = symm.rendezvous(self.buf, pg)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.generation = 0
+
+    def publish(self, v16: torch.Tensor) -> int:
+        self.hdl.barrier(channel=0)  # every rank is done reading the previous step's shards
+        self.buf.copy_(v16)
+        self.hdl.barrier(channel=1)  # every shard is in place
+        self.generation += 1
+        return self.generation
+
+
+class PeerShardedInBatchCE(torch.autograd.Function):
+    """ShardedInBatchCE without the all-gather: the item shards are read from the peers' symmetric buffers."""
+
+    @staticmethod
+    def forward(ctx, U, V, group, peers: _PeerItemBuffers):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        B, d = U.shape
+        U_op, V_op = _CudaKernels.operand(U), _CudaKernels.operand(V)
+        gen = peers.publish(V_op)
+        ce, lse = ops.inbatch_ce_forward_parts(U_op, peers.ptrs, B, peers.buf.stride(0), B, world * B, d, rank * B)
+        ctx.save_for_backward(U_op, lse)
+        ctx.meta = (B, d, rank, world, group, peers, gen)
+        return ce
+
+    @staticmethod
+    def backward(ctx, g):
+        U_op, lse = ctx.saved_tensors
+        B, d, rank, world, group, peers, gen = ctx.meta
+        if gen != peers.generation:
+            raise RuntimeError("the peer item buffers were overwritten by a later forward; run backward before the next "
+                               "forward or disable peer-memory scoring (TT_B200_PEER_CE=0)")
+        dU, dV_all = ops.inbatch_ce_backward_parts(U_op, peers.ptrs, B, peers.buf.stride(0), B, world * B, d, rank * B,
+                                                   lse, g.contiguous().float())
+        dV = _reduce_scatter_sum(dV_all, rank, world, group)
+        return dU, dV, None, None
+
+
 class DataParallelContext:
-    def __init__(self, group=None, kernels=None):
+    def __init__(self, group=None, kernels=None, peer_memory=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (launch with torchrun, one process per GPU)")
         self.group = group
@@ -90,11 +143,24 @@ class DataParallelContext:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._presynced = set()  # ids of parameters whose gradient is already the global sum after backward
+        if peer_memory is None:
+            import os
+
+            peer_memory = os.environ.get("TT_B200_PEER_CE", "0") == "1"
+        self.peer_memory = bool(peer_memory) and kernels is None
+        self._peers = None
 
     def compute_training_loss(self, model, user_embedding, item_embeddings, position, labels):
         """Sharded version of TwoTowerBaseRetrieval.compute_training_loss (reference :279-347); the
         debias_net_user_value hook is called exactly as in the single-GPU path."""
-        ce = ShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self.kernels)  # [B_loc]
+        if self.peer_memory and user_embedding.shape[0] % 128 == 0:
+            B, dcols = item_embeddings.shape
+            pitch = (dcols + 7) // 8 * 8
+            if self._peers is None or tuple(self._peers.buf.shape) != (B, pitch):
+                self._peers = _PeerItemBuffers(self.group, B, pitch, item_embeddings.device)
+            ce = PeerShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self._peers)  # [B_loc]
+        else:
+            ce = ShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self.kernels)  # [B_loc]
         net_user_value = torch.sum(labels * model.user_value_weights, dim=-1)
         net_user_value, additional_loss = model.debias_net_user_value(
             net_user_value=net_user_value, position=position, user_embedding=user_embedding
@@ -154,9 +220,11 @@ class DataParallelContext:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
 
 
-def enable_data_parallel(model, group=None, kernels=None) -> DataParallelContext:
-    """Shard `model.compute_training_loss` over the process group (see module docstring)."""
-    ctx = DataParallelContext(group, kernels)
+def enable_data_parallel(model, group=None, kernels=None, peer_memory=None) -> DataParallelContext:
+    """Shard `model.compute_training_loss` over the process group (see module docstring).  peer_memory=True (or
+    TT_B200_PEER_CE=1) replaces the NCCL all-gather of the item embeddings by in-kernel TMA reads of the peers'
+    symmetric-memory buffers."""
+    ctx = DataParallelContext(group, kernels, peer_memory)
     model._dp = ctx
     return ctx
 

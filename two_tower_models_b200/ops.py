@@ -968,3 +968,45 @@ class TowerSetFunction(torch.autograd.Function):
             dextra = d["dX16"][:, 2 * D8:2 * D8 + E].float() if d["has_extra"] else None
             grads += [None, dfeats, dextra, dtable, d["dW0"], d["db0"], d["dW1"], d["dXsum"][D8:D8 + D], dWt, d["dbt"]]
         return (None, None, *grads)
+
+
+def _part_array(parts):
+    import ctypes
+
+    return (ctypes.c_void_p * len(parts))(*[int(p) for p in parts])
+
+
+def inbatch_ce_forward_parts(U16, v_ptrs, rows_per_part, ldv, B, N, d, target_offset=0):
+    """ce, lse of U against V = [parts...] given as device pointers (possibly peer memory), see tt_inbatch_ce_fwd_parts."""
+    ce = torch.empty(B, dtype=torch.float32, device=U16.device)
+    lse = torch.empty(B, dtype=torch.float32, device=U16.device)
+    ws = _ce_workspace(B, N, d, U16.device)
+    with _span("inbatch_ce_fwd"):
+        _native.check(
+            _native.lib().tt_inbatch_ce_fwd_parts(U16.data_ptr(), U16.stride(0), _part_array(v_ptrs), len(v_ptrs),
+                                                  rows_per_part, ldv, B, N, d, target_offset, ce.data_ptr(), lse.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), _stream()),
+            "inbatch_ce_fwd_parts",
+        )
+    return ce, lse
+
+
+def inbatch_ce_backward_parts(U16, v_ptrs, rows_per_part, ldv, B, N, d, target_offset, lse, g):
+    dev = U16.device
+    dU = torch.empty((B, d), dtype=torch.float32, device=dev)
+    dV = torch.empty((N, d), dtype=torch.float32, device=dev)
+    dU16 = torch.empty((B, _r8(d)), dtype=_BF16, device=dev)
+    ws = _ce_workspace(B, N, d, dev)
+    cs = torch.zeros((2, d), dtype=torch.float32, device=dev) if d <= 128 else None
+    with _span("inbatch_ce_bwd"):
+        _native.check(
+            _native.lib().tt_inbatch_ce_bwd_parts(
+                U16.data_ptr(), U16.stride(0), _part_array(v_ptrs), len(v_ptrs), rows_per_part, ldv, B, N, d, target_offset,
+                lse.data_ptr(), g.data_ptr(), dU.data_ptr(), dU.stride(0), dU16.data_ptr(), dU16.stride(0),
+                dV.data_ptr(), dV.stride(0), None, 0, _ptr(cs), None, ws.data_ptr(), ws.numel(), _stream()),
+            "inbatch_ce_bwd_parts",
+        )
+    dU._tt_bf16 = dU16
+    if cs is not None:
+        dU._tt_colsum = cs[0]
+    return dU, dV
