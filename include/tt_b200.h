@@ -147,6 +147,23 @@ int tt_inbatch_ce_bwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64
 int tt_weighted_loss(const float* ce, const float* labels, int64_t ld_labels, const float* weights, int64_t B, int64_t T,
                      float* loss, float* g, void* stream);
 
+/* tt_inbatch_ce_fwd and tt_weighted_loss in two launches instead of three: the kernel that merges the CE partials
+ * also forms nuv_i = max(labels_i . weights, 1e-6) and reduces the weighted mean - the whole of compute_training_loss
+ * with the identity hook (reference src/two_tower_base_retrieval.py:279-347).  Writes ce[B], lse[B], *loss,
+ * g[i] = nuv_i (UNnormalised) and *g_norm = 1 / (max_i nuv_i * B), so that d loss / d ce[i] = g[i] * *g_norm. */
+int tt_inbatch_ce_loss_fwd(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N,
+                           int64_t d, int64_t target_offset, const float* labels, int64_t ld_labels,
+                           const float* weights, int64_t T, float* ce, float* lse, float* loss, float* g, float* g_norm,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+/* tt_inbatch_ce_bwd with g multiplied by the DEVICE scalars *g_scale and *g_scale2 (each may be NULL = 1): the
+ * incoming gradient of the scalar loss and *g_norm above are applied inside the kernels instead of by separate
+ * elementwise launches. */
+int tt_inbatch_ce_bwd_scaled(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N,
+                             int64_t d, int64_t target_offset, const float* lse, const float* g, const float* g_scale,
+                             const float* g_scale2, float* dU_f32, int64_t lddu, void* dU_bf16, int64_t lddu16,
+                             float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
+                             float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- brute-force MIPS ------------------------------------------------------------------------ */
 
 /* Scratch bytes needed by tt_mips_topk for this shape on the current device. */

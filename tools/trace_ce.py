@@ -28,7 +28,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "fwd":
 # only the dU pass (dV outputs NULL) so that the trace is not overwritten by the second pass
 dU = torch.empty(B, d, device=dev); ws = ops._ce_workspace(B, N, d, dev)
 rc = lib.tt_inbatch_ce_bwd(U.data_ptr(), U.stride(0), V.data_ptr(), V.stride(0), B, N, d, 0, lse.data_ptr(), g.data_ptr(),
-                           dU.data_ptr(), dU.stride(0), None, 0, None, 0, None, 0, ws.data_ptr(), ws.numel(),
+                           dU.data_ptr(), dU.stride(0), None, 0, None, 0, None, 0, None, None, ws.data_ptr(), ws.numel(),
                            torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 c = ct.cpu().view(148, 4); c = c[c[:, 0] > 0]

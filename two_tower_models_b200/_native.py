@@ -67,6 +67,9 @@ SIGNATURES = {
     "tt_inbatch_ce_fwd_parts": (I32, [P, I64, P, I32, I64, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd_parts": (I32, [P, I64, P, I32, I64, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64,
                                       P, P, P, I64, P]),
+    "tt_inbatch_ce_loss_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, I64, P, I64, P, P, P, P, P, P, I64, P]),
+    "tt_inbatch_ce_bwd_scaled": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I64, P, I64, P, I64, P, I64, P, P,
+                                       P, I64, P]),
     "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),

@@ -241,6 +241,23 @@ int tt_inbatch_ce_bwd_parts(const void* U, int64_t ldu, const void* const* Vp, i
                               lddv, dV16, lddv16, dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream));
 }
 
+int tt_inbatch_ce_loss_fwd(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                           int64_t target_offset, const float* labels, int64_t ldl, const float* weights, int64_t T,
+                           float* ce, float* lse, float* loss, float* g, float* g_norm, void* ws, int64_t ws_bytes,
+                           void* stream) {
+  TT_CHECK(labels != nullptr && weights != nullptr && loss != nullptr && g != nullptr && g_norm != nullptr, "tt_inbatch_ce_loss_fwd: null argument");
+  return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, loss, g, g_norm,
+                             ws, (size_t)ws_bytes, S(stream));
+}
+int tt_inbatch_ce_bwd_scaled(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                             int64_t target_offset, const float* lse, const float* g, const float* g_scale,
+                             const float* g_scale2, float* dU,
+                             int64_t lddu, void* dU16, int64_t lddu16, float* dV, int64_t lddv, void* dV16, int64_t lddv16,
+                             float* dU_colsum, float* dV_colsum, void* ws, int64_t ws_bytes, void* stream) {
+  return inbatch_ce_bwd(U, ldu, V, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16, lddv16,
+                        dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream), g_scale, g_scale2);
+}
+
 int tt_weighted_loss(const float* ce, const float* labels, int64_t ldl, const float* weights, int64_t B, int64_t T,
                      float* loss, float* g, void* stream) {
   return weighted_loss(ce, labels, ldl, weights, B, T, loss, g, S(stream));

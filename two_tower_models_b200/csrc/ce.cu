@@ -36,9 +36,15 @@ struct CeFwdArgs {
   long long Bpad;
   float* part_m;
   float* part_s;
-  float* diag;
+  struct LossSync* sync;  // ticket of the fused combine+loss kernel, zeroed here
+  unsigned skew_ns;       // start delay of the odd epilogue groups
   long long* trace;  // bring-up (TT_CE_TRACE)
+  int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip the maximum, bit2 skip the whole tile update
 };
+
+// epilogue column groups of the forward kernel: FWD_EG x 4 warps, each thread owns 128 / FWD_EG columns of a row
+static constexpr int FWD_EG = 2;
+static constexpr int FWD_THREADS = 128 + FWD_EG * 128;
 
 template <int DP>
 struct CeFwdCfg {
@@ -55,8 +61,19 @@ struct CeFwdCfg {
 // [64 e, 64 e + 64)), so all 8 epilogue warps are busy on the tile that is ready while the UMMA warp runs up
 // to NS - 1 tiles ahead.  A row's running (max, sum-exp) is therefore split over two threads; the combine
 // kernel merges the (slot, group) partials.
+// bring-up hooks (clock64 timelines, partial epilogues) exist only when compiled with -DTT_CE_BRINGUP
+#ifdef TT_CE_BRINGUP
+#define CE_FWD_STAMP(tile, which)                                                                              \
+  do {                                                                                                         \
+    if (a.trace && !(a.dbg & 16) && blockIdx.x == 0 && (tile) < 64 && q == 0 && lane == 0 && e < 2)              \
+      a.trace[((2 + e) * 64 + (tile)) * 2 + (which)] = clock64();                                               \
+  } while (0)
+#else
+#define CE_FWD_STAMP(tile, which) do { } while (0)
+#endif
+
 template <int DP>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TmapSet tmy, const CeFwdArgs a) {
   using Cfg = CeFwdCfg<DP>;
   constexpr int BN = Cfg::BN, NS = Cfg::NS;
@@ -78,6 +95,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
     tma_prefetch_desc(&tmx);
     for (int p = 0; p < tmy.n; ++p) tma_prefetch_desc(&tmy.m[p]);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 96) *reinterpret_cast<unsigned int*>(a.sync) = 0u;  // workspace is uninitialised
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
@@ -87,7 +105,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
+      mbar_init(&s_empty[i], 4 * FWD_EG);
     }
     fence_barrier_init();
   }
@@ -96,6 +114,14 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+#ifdef TT_CE_BRINGUP
+  if ((a.dbg & 16) && a.trace && blockIdx.x == 0 && threadIdx.x == 128) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[0] = clock64();
+    a.trace[1] = (long long)gt;
+  }
+#endif
 
   if (warp == 0) {
     if (lane == 0) {
@@ -133,12 +159,18 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
         mbar_wait(x_full, xs & 1);
         for (int j = j0; j < j1; ++j, ++t) {
           const uint32_t buf = t % NS, use = t / NS;
-          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 0] = clock64();
+#ifdef TT_CE_BRINGUP
+          if (a.trace && !(a.dbg & 16) && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 0] = clock64();
+#endif
           mbar_wait(&y_full[stage], phase);
-          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(1 * 64 + t) * 2 + 0] = clock64();
+#ifdef TT_CE_BRINGUP
+          if (a.trace && !(a.dbg & 16) && blockIdx.x == 0 && t < 64 && leader) a.trace[(1 * 64 + t) * 2 + 0] = clock64();
+#endif
           mbar_wait(&s_empty[buf], (use & 1) ^ 1);
           tc_fence_after();
-          if (a.trace && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 1] = clock64();
+#ifdef TT_CE_BRINGUP
+          if (a.trace && !(a.dbg & 16) && blockIdx.x == 0 && t < 64 && leader) a.trace[(0 * 64 + t) * 2 + 1] = clock64();
+#endif
           const uint64_t dy = desc_advance(dy0, stage * Cfg::Y_BYTES);
 #pragma unroll
           for (int k = 0; k < DP / 16; ++k)
@@ -153,79 +185,130 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
       }
     }
   } else if (warp >= 4) {
-    const int e = (warp - 4) >> 2;  // column half of every tile
+    const int e = (warp - 4) >> 2;  // column group of every tile
     const int q = warp & 3;         // TMEM lane quarter
+    constexpr int CW = BN / FWD_EG;  // columns per thread and tile
+    constexpr int NL = CW / 32;      // 32-column TMEM loads per thread and tile
+    static_assert(BN == 128 && (CW == 32 || CW == 64), "epilogue column groups");
     SegIter it(a.T, a.total, a.CT);
     int r, j0, j1;
     uint32_t t = 0;
-    while (it.next(r, j0, j1)) {
-      const long long row = (long long)r * 128 + q * 32 + lane;
-      const bool valid = row < a.B;
-      const long long tgt = row + a.target_offset;
-      float m = -INFINITY, s = 0.f;
-      for (int j = j0; j < j1; ++j, ++t) {
-        const uint32_t buf = t % NS, use = t / NS;
-        mbar_wait(&s_full[buf], use & 1);
-        tc_fence_after();
-        if (a.trace && blockIdx.x == 0 && t < 64 && q == 0 && lane == 0) a.trace[((2 + e) * 64 + t) * 2 + 0] = clock64();
-        // online (max, sum-exp) update with the 32 scores of tile columns [c*32, c*32+32)
-        auto consume = [&](float* v, int c) {
-          const long long n0 = (long long)j * BN + c * 32;
-          if (n0 >= a.N) return;
-          if (n0 + 32 > a.N) {
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + e * CW;
+    const uint32_t sfull0 = smem_u32(s_full), sempty0 = smem_u32(s_empty);
+    // The per-tile bookkeeping is kept to a handful of instructions (32-bit indices, tile-level special-case tests,
+    // bring-up hooks compiled out): with it at ~180 instructions per warp and tile the epilogue was issue-bound at
+    // half of the MUFU rate (profiles/r01_ce_fwd_inst_mix.txt).
+    // TMEM -> registers of this thread's CW scores of tile `tt` (asynchronous: complete after tmem_wait_ld)
+    auto load_tile = [&](uint32_t tt, float* x) {
+      const uint32_t buf = tt & (NS - 1);
+      mbar_wait_addr(sfull0 + buf * 8, (tt / NS) & 1);
+      tc_fence_after();
+      CE_FWD_STAMP(tt, 0);
+#ifdef TT_CE_BRINGUP
+      if (a.dbg & 32) {  // synthetic scores instead of the TMEM load
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + i >= a.N) v[i] = -INFINITY;
-          }
-          if (valid && tgt >= n0 && tgt < n0 + 32) {
-            float dg = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + i == tgt) dg = v[i];
-            a.diag[row] = dg;
-          }
-          // chunk maximum as a tree (4 independent chains), then one rescale of the running sum
-          float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
-#pragma unroll
-          for (int i = 8; i < 32; i += 4) {
-            c0 = fmaxf(c0, v[i]); c1 = fmaxf(c1, v[i + 1]); c2 = fmaxf(c2, v[i + 2]); c3 = fmaxf(c3, v[i + 3]);
-          }
-          const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-          const float m_new = fmaxf(m, cm * LOG2E);
-          const float ms = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked so far: avoid inf - inf
-          s *= ex2f(m - ms);
-          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            acc0 += ex2f(fmaf(v[i], LOG2E, -ms));
-            acc1 += ex2f(fmaf(v[i + 1], LOG2E, -ms));
-            acc2 += ex2f(fmaf(v[i + 2], LOG2E, -ms));
-            acc3 += ex2f(fmaf(v[i + 3], LOG2E, -ms));
-          }
-          s += (acc0 + acc1) + (acc2 + acc3);
-          m = m_new;
-        };
-        static_assert(BN == 128, "two 32-column chunks per epilogue group");
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * 64;
-        float v0[32], v1[32];
-        tmem_ld32(taddr, v0);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 32, v1);  // in flight while the first chunk is reduced
-        consume(v0, e * 2);
-        tmem_wait_ld();
-        consume(v1, e * 2 + 1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[buf]);
-        if (a.trace && blockIdx.x == 0 && t < 64 && q == 0 && lane == 0) a.trace[((2 + e) * 64 + t) * 2 + 1] = clock64();
+        for (int i = 0; i < CW; ++i) x[i] = (float)(int)(tt * 7 + i) * 0.01f - 3.f;
+        return;
       }
+#endif
+#pragma unroll
+      for (int l = 0; l < NL; ++l) tmem_ld32(lane_addr + buf * BN + l * 32, x + l * 32);
+    };
+    // the score buffer goes back to the UMMA warp as soon as its values sit in registers
+    auto release = [&](uint32_t tt) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(sempty0 + (tt & (NS - 1)) * 8);
+    };
+    static_assert((NS & (NS - 1)) == 0, "NS must be a power of two");
+    // The warps that share a scheduler (same q, different column group) would otherwise run in lock step - both in
+    // their MUFU phase, then both in their FMA/max phase - and the two pipes never overlap.  Starting every second
+    // group about half a tile late keeps them out of phase for the rest of the kernel (the score buffers give slack).
+    if (a.skew_ns > 0 && (e & 1)) __nanosleep(a.skew_ns);
+    while (it.next(r, j0, j1)) {
+      const int row = r * 128 + q * 32 + lane;
+      const bool valid = row < a.B;
+      // the (only) tile with columns past N is the one special case; the positive's logit is not picked out of the
+      // score tiles at all - the merge kernel recomputes that one dot product per row from the operands
+      const int jpart = (a.N % BN) != 0 ? a.N / BN : -1;
+      float m = -INFINITY, s = 0.f;
+      // online (max, sum-exp) update with this thread's CW scores of a tile: one maximum and one rescale, then CW
+      // independent exponentials (in place, back to back on the MUFU pipe) and their sum
+      auto process = [&](float* x, int j) {
+#ifdef TT_CE_BRINGUP
+        if (a.dbg & 4) { s += x[0]; return; }
+#endif
+        if (j == jpart) {
+          asm volatile("");  // keep this a branch: if-converted it costs 2 * CW instructions on every tile
+          const int n0 = j * BN + e * CW;
+#pragma unroll
+          for (int i = 0; i < CW; ++i)
+            if (n0 + i >= a.N) x[i] = -INFINITY;
+        }
+        float c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = fmaxf(x[u], x[u + 4]);
+#pragma unroll
+        for (int i = 8; i < CW; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c[u] = fmaxf(c[u], x[i + u]);
+        }
+        const float cm = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
+        const float m_new = fmaxf(m, cm * LOG2E);
+        const float ms = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked so far: avoid inf - inf
+        s *= ex2f(m - ms);
+#ifdef TT_CE_BRINGUP
+        if (a.dbg & 1) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) x[i] = fmaf(x[i], LOG2E, -ms);
+        } else
+#endif
+        {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) x[i] = ex2f(fmaf(x[i], LOG2E, -ms));
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < CW; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += x[i + u];
+        }
+        s += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        m = m_new;
+      };
+      const int n = j1 - j0;
+      float xa[CW], xb[CW];
+      load_tile(t, xa);
+      for (int i = 0; i < n; i += 2) {
+        tmem_wait_ld();
+        release(t + i);
+        if (i + 1 < n) load_tile(t + i + 1, xb);
+        process(xa, j0 + i);
+        CE_FWD_STAMP(t + i, 1);
+        if (i + 1 < n) {
+          tmem_wait_ld();
+          release(t + i + 1);
+          if (i + 2 < n) load_tile(t + i + 2, xa);
+          process(xb, j0 + i + 1);
+          CE_FWD_STAMP(t + i + 1, 1);
+        }
+      }
+      t += n;
       if (valid) {
         const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
-        const long long o = (long long)(slot * 2 + e) * a.Bpad + row;
+        const long long o = (long long)(slot * FWD_EG + e) * a.Bpad + row;
         a.part_m[o] = m;
         a.part_s[o] = s;
       }
     }
+#ifdef TT_CE_BRINGUP
+    if ((a.dbg & 16) && a.trace && blockIdx.x == 0 && threadIdx.x == 128) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      a.trace[2] = clock64();
+      a.trace[3] = (long long)gt;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -236,25 +319,141 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
   }
 }
 
+// The positive's logit U_i . V_{i+off}: fp32 dot product of the same bf16 operands the score tiles were made from
+// (the tensor cores accumulate the same exact products in fp32, in another order).
+struct DiagOperands {
+  const bf16* U;
+  long long ldu;
+  const bf16* Vp[8];
+  long long rows_per_part, ldv, target_offset;
+  int d;
+};
+__device__ __forceinline__ float positive_logit(const DiagOperands& o, long long row) {
+  const long long t = row + o.target_offset;
+  const long long p = t / o.rows_per_part;
+  const bf16* u = o.U + row * o.ldu;
+  const bf16* v = o.Vp[p] + (t - p * o.rows_per_part) * o.ldv;
+  float acc0 = 0.f, acc1 = 0.f;
+  int k = 0;
+  for (; k + 8 <= o.d; k += 8) {  // rows are 16-byte aligned (operand pitch is a multiple of 8 elements)
+    const uint4 a4 = *reinterpret_cast<const uint4*>(u + k);
+    const uint4 b4 = *reinterpret_cast<const uint4*>(v + k);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
+      acc0 = fmaf(fa.x, fb.x, acc0);
+      acc1 = fmaf(fa.y, fb.y, acc1);
+    }
+  }
+  for (; k < o.d; ++k) acc0 = fmaf(__bfloat162float(u[k]), __bfloat162float(v[k]), acc0);
+  return acc0 + acc1;
+}
+
 __global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, const float* part_m, const float* part_s,
-                                  const float* diag, float* ce, float* lse) {
+                                  const DiagOperands dg, float* ce, float* lse) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= B) return;
   const long long r = row / 128;
   const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
   float M = -INFINITY;
   for (int sl = 0; sl <= last - first; ++sl)
-    for (int e = 0; e < 2; ++e) M = fmaxf(M, part_m[(long long)(sl * 2 + e) * Bpad + row]);
+    for (int e = 0; e < FWD_EG; ++e) M = fmaxf(M, part_m[(long long)(sl * FWD_EG + e) * Bpad + row]);
   float S = 0.f;
   for (int sl = 0; sl <= last - first; ++sl)
-    for (int e = 0; e < 2; ++e) {
-      const long long o = (long long)(sl * 2 + e) * Bpad + row;
+    for (int e = 0; e < FWD_EG; ++e) {
+      const long long o = (long long)(sl * FWD_EG + e) * Bpad + row;
       S += part_s[o] * exp2f(part_m[o] - M);
     }
   const float l = (M + log2f(S)) * LN2;
   lse[row] = l;
-  ce[row] = l - diag[row];
+  ce[row] = l - positive_logit(dg, row);
 }
+
+// combine + value-weighted mean in ONE launch (identity debias hook, reference :322-343).  Every block merges the
+// (max, sum-exp) partials of 256 rows into ce / lse, forms nuv = max(labels . w, 1e-6) and reduces (max nuv,
+// sum ce nuv) over its rows; the last block to finish (atomic ticket) folds the per-block pairs in block order
+// (deterministic) into  loss = sum / (max B)  and  g_norm = 1 / (max B).  The backward kernels take g = nuv and
+// the device scalar g_norm, so the normalised weights never make a separate pass.
+static constexpr int LOSS_MAX_BLOCKS = 1024;
+struct LossSync {
+  unsigned int ticket;
+  unsigned int pad[3];
+  float pmax[LOSS_MAX_BLOCKS];
+  float psum[LOSS_MAX_BLOCKS];
+};
+__global__ void __launch_bounds__(256)
+ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* __restrict__ part_m,
+                       const float* __restrict__ part_s, const DiagOperands dg, float* __restrict__ ce,
+                       float* __restrict__ lse, const float* __restrict__ labels, long long ldl,
+                       const float* __restrict__ uvw, int TL, float inv_rows, float* __restrict__ loss,
+                       float* __restrict__ g, float* __restrict__ g_norm, LossSync* sync) {
+  __shared__ float red_m[8], red_s[8];
+  __shared__ unsigned int last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row = (long long)blockIdx.x * blockDim.x + tid;
+  float nuv = 0.f, cw = 0.f;
+  if (row < B) {
+    const long long r = row / 128;
+    const int first = (int)((r * CT) / T), last_slot = (int)(((r + 1) * CT - 1) / T);
+    float M = -INFINITY;
+    for (int sl = 0; sl <= last_slot - first; ++sl)
+      for (int e = 0; e < FWD_EG; ++e) M = fmaxf(M, part_m[(long long)(sl * FWD_EG + e) * Bpad + row]);
+    float S = 0.f;
+    for (int sl = 0; sl <= last_slot - first; ++sl)
+      for (int e = 0; e < FWD_EG; ++e) {
+        const long long o = (long long)(sl * FWD_EG + e) * Bpad + row;
+        S += part_s[o] * exp2f(part_m[o] - M);
+      }
+    const float l = (M + log2f(S)) * LN2;
+    const float c = l - positive_logit(dg, row);
+    lse[row] = l;
+    ce[row] = c;
+    for (int t = 0; t < TL; ++t) nuv = fmaf(labels[row * ldl + t], uvw[t], nuv);
+    nuv = fmaxf(nuv, 0.000001f);
+    g[row] = nuv;
+    cw = c * nuv;
+  }
+  float mx = nuv;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    cw += __shfl_xor_sync(0xffffffffu, cw, o);
+  }
+  if (lane == 0) { red_m[warp] = mx; red_s[warp] = cw; }
+  __syncthreads();
+  if (tid == 0) {
+    float m = red_m[0], sm = red_s[0];
+    for (int w = 1; w < 8; ++w) { m = fmaxf(m, red_m[w]); sm += red_s[w]; }
+    sync->pmax[blockIdx.x] = m;
+    sync->psum[blockIdx.x] = sm;
+    __threadfence();
+    last = (atomicAdd(&sync->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (last && warp == 0) {
+    __threadfence();
+    float m = 0.f, sm = 0.f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) {  // lane-strided, then a fixed-order butterfly: deterministic
+      m = fmaxf(m, __ldcg(&sync->pmax[i]));
+      sm += __ldcg(&sync->psum[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
+    if (lane == 0) {
+      const float gn = inv_rows / m;
+      *loss = sm * gn;
+      *g_norm = gn;
+      sync->ticket = 0;  // ready for the next launch (CUDA-graph replay)
+    }
+  }
+}
+
+__global__ void set_scalar_kernel(float* p, float v) { *p = v; }
 
 static int pick_dp(long long d) { return d <= 64 ? 64 : (d <= 128 ? 128 : 256); }
 
@@ -276,7 +475,7 @@ static int make_tmap_set(TmapSet* t, const void* const* parts, int np, long long
 }
 
 static size_t fwd_ws_bytes(const Sched& s, long long Bpad) {
-  return (size_t)(2 * (size_t)s.max_slots * 2 * Bpad + Bpad) * sizeof(float);
+  return (size_t)(2 * (size_t)s.max_slots * FWD_EG * Bpad) * sizeof(float) + sizeof(LossSync);
 }
 static size_t bwd_ws_bytes(const Sched& s, int DP) { return (size_t)s.max_slots * s.XT * 128 * DP * sizeof(float); }
 
@@ -300,7 +499,7 @@ static int launch_ce_fwd(const CUtensorMap& tx, const TmapSet& ty, const CeFwdAr
     configured = true;
   }
   KernelSpan span("ce_fwd_kernel", st);
-  ce_fwd_kernel<DP><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
+  ce_fwd_kernel<DP><<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -314,6 +513,14 @@ int inbatch_ce_fwd(const void* U, long long ldu, const void* V, long long ldv, l
 int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
                          long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
                          float* lse, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return inbatch_ce_loss_fwd(U, ldu, Vp, np, rows_per_part, ldv, B, N, d, target_offset, ce, lse, nullptr, 0, nullptr, 0,
+                             nullptr, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                        long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
+                        float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
+                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const void* V = Vp[0];
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_fwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_fwd: embedding dim %lld > 256 is not supported", d);
@@ -329,10 +536,16 @@ int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, in
   a.B = (int)B; a.N = (int)N; a.target_offset = target_offset;
   a.T = s.T; a.total = s.total; a.CT = s.CT; a.Bpad = Bpad;
   a.part_m = (float*)ws;
-  a.part_s = a.part_m + (size_t)s.max_slots * 2 * Bpad;
-  a.diag = a.part_s + (size_t)s.max_slots * 2 * Bpad;
+  a.part_s = a.part_m + (size_t)s.max_slots * FWD_EG * Bpad;
+  a.sync = reinterpret_cast<LossSync*>(a.part_s + (size_t)s.max_slots * FWD_EG * Bpad);
+  DiagOperands dgo;
+  dgo.U = (const bf16*)U; dgo.ldu = ldu; dgo.ldv = ldv; dgo.target_offset = target_offset; dgo.d = (int)d;
+  dgo.rows_per_part = np == 1 ? N : rows_per_part;
+  for (int p = 0; p < 8; ++p) dgo.Vp[p] = (const bf16*)Vp[p < np ? p : 0];
   a.trace = nullptr;
   if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
+  a.dbg = getenv("TT_CE_DBG") ? atoi(getenv("TT_CE_DBG")) : 0;
+  a.skew_ns = getenv("TT_CE_SKEW_NS") ? (unsigned)atoi(getenv("TT_CE_SKEW_NS")) : 300u;
   CUtensorMap tx;
   TmapSet ty;
   int rc = make_tmap_bf16(&tx, U, d, B, ldu, 64, 128);
@@ -343,10 +556,29 @@ int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, in
   else if (DP == 128) rc = launch_ce_fwd<128>(tx, ty, a, s.grid, stream);
   else rc = launch_ce_fwd<256>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
-  KernelSpan span("ce_combine_kernel", stream);
-  ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, a.diag, ce, lse);
-  TT_CUDA(cudaGetLastError());
-  count_launch();
+  const long long loss_blocks = (B + 255) / 256;
+  if (labels != nullptr && loss_blocks <= LOSS_MAX_BLOCKS) {
+    TT_CHECK(TL > 0 && ldl >= TL && uvw && loss && g && g_norm, "inbatch_ce_loss_fwd: bad label arguments");
+    KernelSpan span("ce_combine_loss_kernel", stream);
+    ce_combine_loss_kernel<<<(unsigned)loss_blocks, 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, dgo, ce,
+                                                                      lse, labels, ldl, uvw, (int)TL, 1.f / (float)B, loss, g,
+                                                                      g_norm, a.sync);
+    TT_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  {
+    KernelSpan span("ce_combine_kernel", stream);
+    ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, dgo, ce, lse);
+    TT_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (labels != nullptr) {  // very large batch: separate weighted-mean launch; g is already normalised
+    set_scalar_kernel<<<1, 1, 0, stream>>>(g_norm, 1.f);
+    TT_CUDA(cudaGetLastError());
+    count_launch();
+    return weighted_loss(ce, labels, ldl, uvw, B, TL, loss, g, stream);
+  }
   return 0;
 }
 
@@ -407,7 +639,8 @@ ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
 template <int DP>
 static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long x_rows_per_part, long long ldx, long long xr,
                        const void* const* Yp, int nyp, long long y_rows_per_part, long long ldy,
-                       long long yr, long long d, long long diag_shift, const float* g, const float* lse, float* out32,
+                       long long yr, long long d, long long diag_shift, const float* g, const float* g_scale,
+                       const float* g_scale2, const float* lse, float* out32,
                        long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
                        ReduceJob& job, cudaStream_t stream) {
   constexpr int BN = DP == 256 ? 64 : 128;
@@ -416,7 +649,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
   CeBwdArgs a;
   a.XR = (int)xr; a.YR = (int)yr; a.diag_shift = diag_shift;
   a.T = s.T; a.total = s.total; a.CT = s.CT;
-  a.g = g; a.lse = lse;
+  a.g = g; a.g_scale = g_scale; a.g_scale2 = g_scale2; a.lse = lse;
   a.partial = (float*)ws;
   a.slot_stride = (long long)s.XT * 128 * DP;
   a.trace = nullptr;
@@ -442,16 +675,17 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
                    long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, float* dU_colsum,
-                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream, const float* g_scale,
+                   const float* g_scale2) {
   return inbatch_ce_bwd_parts(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, lse, g, dU, lddu, dU16, lddu16, dV, lddv, dV16,
-                              lddv16, dU_colsum, dV_colsum, ws, ws_bytes, stream);
+                              lddv16, dU_colsum, dV_colsum, ws, ws_bytes, stream, g_scale, g_scale2);
 }
 
 int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
                          long long ldv, long long B, long long N, long long d, long long target_offset, const float* lse,
                          const float* g, float* dU, long long lddu, void* dU16, long long lddu16, float* dV, long long lddv,
                          void* dV16, long long lddv16, float* dU_colsum, float* dV_colsum, void* ws, size_t ws_bytes,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const float* g_scale, const float* g_scale2) {
   const void* V = Vp[0];
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_bwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_bwd: embedding dim %lld > 256 is not supported", d);
@@ -469,10 +703,10 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
 #define TT_PASS(DPV)                                                                                                 \
   do {                                                                                                               \
     if (wantU)                                                                                                       \
-      rc = ce_bwd_pass<DPV>(false, &U, 1, B, ldu, B, Vp, np, rows_per_part, ldv, N, d, target_offset, g, lse, dU, lddu, dU16, \
+      rc = ce_bwd_pass<DPV>(false, &U, 1, B, ldu, B, Vp, np, rows_per_part, ldv, N, d, target_offset, g, g_scale, g_scale2, lse, dU, lddu, dU16, \
                             lddu16, dU_colsum, ws, offB, ja, stream);                                                \
     if (rc == 0 && wantV)                                                                                            \
-      rc = ce_bwd_pass<DPV>(true, Vp, np, rows_per_part, ldv, N, &U, 1, B, ldu, B, d, -target_offset, g, lse, dV, lddv, dV16, \
+      rc = ce_bwd_pass<DPV>(true, Vp, np, rows_per_part, ldv, N, &U, 1, B, ldu, B, d, -target_offset, g, g_scale, g_scale2, lse, dV, lddv, dV16, \
                             lddv16, dV_colsum, (char*)ws + offB, ws_bytes - offB, jb, stream);                       \
   } while (0)
   if (DP == 64) TT_PASS(64);

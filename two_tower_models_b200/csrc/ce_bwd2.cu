@@ -219,6 +219,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     uint32_t t = 0, xs = 0;
     const uint32_t prow = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float gs = (a.g_scale != nullptr ? __ldg(a.g_scale) : 1.f) * (a.g_scale2 != nullptr ? __ldg(a.g_scale2) : 1.f);
     while (it.next(r, j0, j1)) {
       const long long row = (long long)r * 128 + prow;
       const bool valid = row < a.XR;
@@ -243,7 +244,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       }
       float rs = 1.f, rl = 0.f;
       if (!COLSTATS) {
-        rs = valid ? a.g[row] : 0.f;
+        rs = valid ? a.g[row] * gs : 0.f;
         rl = valid ? a.lse[row] * LOG2E : 0.f;
       }
       const long long tgt = row + a.diag_shift;
@@ -255,7 +256,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
             const int cidx = e * (BN / 2) + wg_tid;
             const long long col = (long long)j * BN + cidx;
             const bool cv = col < a.YR;
-            scol[cidx] = make_float2(cv ? a.g[col] : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
+            scol[cidx] = make_float2(cv ? a.g[col] * gs : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
         }

@@ -62,6 +62,8 @@ struct CeBwdArgs {
   long long T, total;
   int CT;
   const float* g;    // upstream dL/dce, indexed by user
+  const float* g_scale;   // optional device scalars multiplied into g (incoming d loss; weight normalisation
+  const float* g_scale2;  // 1 / (max nuv * B) of the fused weighted mean), or null
   const float* lse;  // indexed by user
   float* partial;    // [max_slots][XT*128][DP]
   long long slot_stride;

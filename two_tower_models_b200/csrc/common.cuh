@@ -81,21 +81,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// the same on a shared-memory ADDRESS (callers that keep barrier addresses in registers)
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 // Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU box.
 #ifndef TT_MBAR_TIMEOUT_CYCLES
 #define TT_MBAR_TIMEOUT_CYCLES (6000000000LL)  // ~3 s at 2 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  if (mbar_try_wait_addr(bar_addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(bar_addr, parity)) {
     if (clock64() - t0 > TT_MBAR_TIMEOUT_CYCLES) {
       printf("tt_b200: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+             blockIdx.z, threadIdx.x, bar_addr, parity);
       __trap();
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -247,6 +263,21 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
 }
+
+// Scheduling fence over 16 register values: everything that produces them is issued before, everything that consumes
+// them after.  Used to keep ptxas from chaining each MUFU result straight into a dependent add (which serialises the
+// MUFU latency) when register pressure is high: exponentials first, back to back, sums afterwards.
+__device__ __forceinline__ void sched_fence16(float* v) {
+  asm volatile(""
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
+}
+
+// Warp-specialised register budgets: a whole warpgroup (4 consecutive warps) gives registers back / takes more.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- misc math --------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2f(float x) {

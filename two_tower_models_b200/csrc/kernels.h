@@ -43,12 +43,18 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
                          long long ldv, long long B, long long N, long long d, long long target_offset, const float* lse,
                          const float* g, float* dU, long long lddu, void* dU16, long long lddu16, float* dV, long long lddv,
                          void* dV16, long long lddv16, float* dU_colsum, float* dV_colsum, void* ws, size_t ws_bytes,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const float* g_scale = nullptr, const float* g_scale2 = nullptr);
+// Forward fused with the value-weighted mean of the identity debias hook (labels != null): the kernel that merges the
+// partials also writes g = nuv (unnormalised weights), *g_norm = 1 / (max nuv * B) and *loss; d loss / d ce = g * g_norm.
+int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
+                        long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
+                        float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
+                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream);
 // dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,
                    long long lddu16, float* dV, long long lddv, void* dV16, long long lddv16, float* dU_colsum,
-                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream);
+                   float* dV_colsum, void* ws, size_t ws_bytes, cudaStream_t stream, const float* g_scale = nullptr, const float* g_scale2 = nullptr);
 
 // MIPS: top-k of Q C^T per query row.
 size_t mips_workspace_bytes(long long Q, long long C, long long d, long long k);

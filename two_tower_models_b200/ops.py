@@ -494,8 +494,9 @@ def inbatch_ce_forward_raw(U16, V16, B, N, d, target_offset=0):
     return ce, lse
 
 
-def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True, colsums=None):
-    """colsums: optional zero-initialised fp32 [2, d] receiving the column sums of dU and dV (d <= 128)."""
+def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True, colsums=None, g_scale=None, g_scale2=None):
+    """colsums: optional zero-initialised fp32 [2, d] receiving the column sums of dU and dV (d <= 128).
+    g_scale, g_scale2: optional one-element fp32 device tensors multiplied into g inside the kernels."""
     dev = U16.device
     dU = torch.empty((B, d), dtype=torch.float32, device=dev)
     dV = torch.empty((N, d), dtype=torch.float32, device=dev)
@@ -504,9 +505,9 @@ def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=
     ws = _ce_workspace(B, N, d, dev)
     with _span("inbatch_ce_bwd"):
         _native.check(
-            _native.lib().tt_inbatch_ce_bwd(
+            _native.lib().tt_inbatch_ce_bwd_scaled(
                 U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, target_offset,
-                lse.data_ptr(), g.data_ptr(), dU.data_ptr(), dU.stride(0), _ptr(dU16),
+                lse.data_ptr(), g.data_ptr(), _ptr(g_scale), _ptr(g_scale2), dU.data_ptr(), dU.stride(0), _ptr(dU16),
                 dU16.stride(0) if want_bf16 else 0, dV.data_ptr(), dV.stride(0), _ptr(dV16),
                 dV16.stride(0) if want_bf16 else 0,
                 None if colsums is None else colsums.data_ptr(), None if colsums is None else colsums.data_ptr() + 4 * d,
@@ -553,6 +554,56 @@ class InBatchCEFunction(torch.autograd.Function):
 
 def inbatch_cross_entropy(U: torch.Tensor, V: torch.Tensor, target_offset: int = 0) -> torch.Tensor:
     return InBatchCEFunction.apply(U, V, target_offset)
+
+
+class InBatchWeightedLossFunction(torch.autograd.Function):
+    """loss = mean(ce(U V^T, diagonal) * clamp(labels @ w, 1e-6) / max(.)): the whole of compute_training_loss with the
+    identity hook (reference :279-347) in two launches forward (scores+softmax statistics, merge+weights+mean) and
+    three backward (dU pass, dV pass, merge); the incoming d loss is applied inside the backward kernels."""
+
+    @staticmethod
+    def forward(ctx, U, V, labels, weights):
+        _need_cuda(U, V, labels, weights)
+        B, d = U.shape
+        N = V.shape[0]
+        if V.shape[1] != d:
+            raise RuntimeError(f"user/item embedding dims differ: {d} vs {V.shape[1]}")
+        U16 = getattr(U, "_tt_bf16", None)
+        V16 = getattr(V, "_tt_bf16", None)
+        if U16 is None:
+            U16 = cast_rows_bf16(_f32c(U))
+        if V16 is None:
+            V16 = cast_rows_bf16(_f32c(V))
+        labels, weights = _f32c(labels), _f32c(weights)
+        dev = U16.device
+        out = torch.empty(3 * B + 2, dtype=torch.float32, device=dev)  # ce | lse | g | loss | g_norm
+        ce, lse, g, loss, g_norm = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:3 * B + 1].view(()), out[3 * B + 1:]
+        ws = _ce_workspace(B, N, d, dev)
+        with _span("inbatch_ce_fwd"):
+            _native.check(
+                _native.lib().tt_inbatch_ce_loss_fwd(
+                    U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, 0, labels.data_ptr(),
+                    labels.stride(0), weights.data_ptr(), labels.shape[1], ce.data_ptr(), lse.data_ptr(),
+                    loss.data_ptr(), g.data_ptr(), g_norm.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "inbatch_ce_loss_fwd",
+            )
+        ctx.save_for_backward(U16, V16, lse, g, g_norm)
+        ctx.dims = (B, N, d)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        U16, V16, lse, g, g_norm = ctx.saved_tensors
+        B, N, d = ctx.dims
+        cs = torch.zeros((2, d), dtype=torch.float32, device=g.device) if d <= 128 else None
+        dU, dV, dU16, dV16 = inbatch_ce_backward_raw(U16, V16, B, N, d, 0, lse, g, colsums=cs,
+                                                     g_scale=_f32c(dloss).reshape(1), g_scale2=g_norm)
+        dU._tt_bf16 = dU16
+        dV._tt_bf16 = dV16
+        if cs is not None:
+            dU._tt_colsum = cs[0]
+            dV._tt_colsum = cs[1]
+        return dU, dV, None, None
 
 
 class WeightedLossFunction(torch.autograd.Function):

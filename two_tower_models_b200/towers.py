@@ -160,15 +160,15 @@ class TwoTowerBaseRetrieval(nn.Module):
         """
         if self._dp is not None:
             return self._dp.compute_training_loss(self, user_embedding, item_embeddings, position, labels)
-        loss = ops.inbatch_cross_entropy(user_embedding, item_embeddings)  # [B]
         if (
             type(self).debias_net_user_value is TwoTowerBaseRetrieval.debias_net_user_value
             and labels.dim() == 2
             and labels.shape[1] == self.user_value_weights.shape[0]
             and not labels.requires_grad
         ):
-            # identity hook: weights, batch max and the weighted mean in one launch
-            return ops.WeightedLossFunction.apply(loss, labels, self.user_value_weights)
+            # identity hook: label weights, batch max and the weighted mean ride in the CE's merge kernel
+            return ops.InBatchWeightedLossFunction.apply(user_embedding, item_embeddings, labels, self.user_value_weights)
+        loss = ops.inbatch_cross_entropy(user_embedding, item_embeddings)  # [B]
         net_user_value = torch.sum(labels * self.user_value_weights, dim=-1)  # [B]
         net_user_value, additional_loss = self.debias_net_user_value(
             net_user_value=net_user_value, position=position, user_embedding=user_embedding
