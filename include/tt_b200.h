@@ -119,6 +119,46 @@ typedef struct tt_gather_problem {
 } tt_gather_problem;
 int tt_gather_rows_bf16_batched(const tt_gather_problem* problems, int32_t count, int32_t* oob_flag, void* stream);
 
+/* ---- fused tower forward -------------------------------------------------------------------- */
+
+/* emb = [table[ids] | Linear(hidden, D)(relu(Linear(F, hidden)(feats)))] Wt^T + bt for `count` (<= 4) towers of the same
+ * shape in ONE launch: the id lookup, both MLP layers, the concatenation (a K-split of the last GEMM) and the tower
+ * Linear run on chip per 128-row tile, hidden activations stay in tensor memory.  Replaces compute_user_embedding /
+ * compute_item_embeddings of the base model (reference src/two_tower_base_retrieval.py:112-219).
+ * Weights are the bf16 copies (w0 [hidden, F], w1 [D, hidden], wt [DI, 2D]); biases fp32.  Besides emb (fp32 and bf16)
+ * the kernel writes the bf16 activations the backward pass needs: feats_bf16 [rows, F], h_bf16 [rows, hidden],
+ * x_bf16 [rows, 2D] = [id_emb | feat_emb].  Supported shapes: tt_tower_fwd_supported() (F = D = DI in {64, 128},
+ * hidden = 256); other shapes use the per-layer entry points above. */
+typedef struct tt_tower_problem {
+  const int64_t* ids;
+  const float* table;
+  int64_t table_rows;
+  const float* feats;
+  int64_t ld_feats;
+  const void* w0_bf16;
+  int64_t ldw0;
+  const float* b0;
+  const void* w1_bf16;
+  int64_t ldw1;
+  const float* b1;
+  const void* wt_bf16;
+  int64_t ldwt;
+  const float* bt;
+  void* feats_bf16;
+  int64_t ld_feats16;
+  void* h_bf16;
+  int64_t ldh;
+  void* x_bf16;
+  int64_t ldx;
+  float* emb_f32;
+  int64_t ld_emb;
+  void* emb_bf16;
+  int64_t ld_emb16;
+  int64_t rows, F, D, DI, hidden;
+} tt_tower_problem;
+int32_t tt_tower_fwd_supported(int64_t F, int64_t D, int64_t DI, int64_t hidden);
+int tt_tower_fwd(const tt_tower_problem* problems, int32_t count, int32_t* oob_flag, void* stream);
+
 /* ---- in-batch sampled-softmax loss ---------------------------------------------------------- */
 
 /* Scratch bytes needed by tt_inbatch_ce_fwd / _bwd for this shape on the current device. */

@@ -99,7 +99,7 @@ def _random_batch(B, IU, II, uhash, ihash, T, seed, H=4):
     )
 
 
-@pytest.mark.parametrize("B,d,F,T", [(512, 64, 64, 1), (1000, 128, 96, 3), (2048, 256, 128, 1)])
+@pytest.mark.parametrize("B,d,F,T", [(512, 64, 64, 1), (1000, 128, 96, 3), (1000, 128, 128, 3), (2048, 256, 128, 1)])
 def test_base_model_matches_oracle(B, d, F, T):
     """Config-1 shape (B=512, d=64) and larger / ragged shapes against the CPU oracle."""
     uhash = ihash = 1000
@@ -112,6 +112,36 @@ def test_base_model_matches_oracle(B, d, F, T):
     m = _build_base(p, uvw)
     loss, u, v = _run(m, batch)
     _check_against(m, loss, u, v, ref_loss, ref_u, ref_v, ref_grads)
+
+
+@pytest.mark.parametrize("B,d", [(300, 128), (130, 64), (1024, 128)])
+def test_fused_tower_kernel_matches_layered_path(B, d, monkeypatch):
+    """tt_tower_fwd (one launch: lookup + MLP + concat + tower Linear on chip) against the per-layer GEMM launches on
+    the same inputs: same bf16 products and fp32 accumulation, so embeddings and the saved bf16 activations agree to
+    fp32 rounding; on integer-grid inputs every intermediate is exact and the two paths are bit-identical."""
+    from two_tower_models_b200 import ops
+
+    F, hash_size = d, 500
+    g = torch.Generator().manual_seed(B + d)
+    grid = lambda *shape: (torch.randint(-8, 9, shape, generator=g).float() / 8.0)
+    for exact in (False, True):
+        rnd = grid if exact else (lambda *shape: torch.randn(*shape, generator=g) * 0.3)
+        ids = torch.randint(0, hash_size, (B,), generator=g).cuda()
+        feats = rnd(B, F).cuda()
+        table = rnd(hash_size, d).cuda()
+        w0, b0, w1, b1 = rnd(256, F).cuda(), rnd(256).cuda(), (rnd(d, 256) / 16).cuda(), rnd(d).cuda()
+        wt, bt = (rnd(d, 2 * d) / 16).cuda(), rnd(d).cuda()
+        outs = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("TT_B200_FUSED_TOWER", fused)
+            assert ops.tower_fused_supported(F, d, d, 256, 0) == (fused == "1")
+            ctx_out = ops.TowerFunction.apply(ids, feats, None, table, w0, b0, w1, b1, wt, bt, ops.PackedWeights(), "t")
+            outs[fused] = (ctx_out.clone(), ctx_out._tt_bf16.clone())
+        torch.cuda.synchronize()
+        if exact:
+            assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][1], outs["0"][1])
+        else:
+            assert rel_fro(outs["1"][0], outs["0"][0]) < 1e-5
 
 
 def test_base_model_edge_cases():

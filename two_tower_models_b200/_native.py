@@ -44,6 +44,20 @@ class GatherProblem(ctypes.Structure):
                 ("dst_bf16", c_void_p), ("ld_dst", c_int64)]
 
 
+class TowerProblem(ctypes.Structure):
+    """struct tt_tower_problem."""
+
+    _fields_ = [
+        ("ids", c_void_p), ("table", c_void_p), ("table_rows", c_int64), ("feats", c_void_p), ("ld_feats", c_int64),
+        ("w0_bf16", c_void_p), ("ldw0", c_int64), ("b0", c_void_p), ("w1_bf16", c_void_p), ("ldw1", c_int64),
+        ("b1", c_void_p), ("wt_bf16", c_void_p), ("ldwt", c_int64), ("bt", c_void_p),
+        ("feats_bf16", c_void_p), ("ld_feats16", c_int64), ("h_bf16", c_void_p), ("ldh", c_int64),
+        ("x_bf16", c_void_p), ("ldx", c_int64), ("emb_f32", c_void_p), ("ld_emb", c_int64),
+        ("emb_bf16", c_void_p), ("ld_emb16", c_int64),
+        ("rows", c_int64), ("F", c_int64), ("D", c_int64), ("DI", c_int64), ("hidden", c_int64),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/tt_b200.h one to one
 SIGNATURES = {
     "tt_abi_version": (I32, []),
@@ -61,6 +75,8 @@ SIGNATURES = {
     "tt_gemm_bf16_batched": (I32, [P, I32, P]),
     "tt_cast_rows_bf16_batched": (I32, [P, I32, P]),
     "tt_gather_rows_bf16_batched": (I32, [P, I32, P, P]),
+    "tt_tower_fwd_supported": (I32, [I64, I64, I64, I64]),
+    "tt_tower_fwd": (I32, [P, I32, P, P]),
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, P, P, I64, P]),

@@ -210,6 +210,21 @@ int tt_gather_rows_bf16_batched(const tt_gather_problem* pr, int32_t count, int3
   return gather_rows_bf16_batched(g, count, oob_flag, S(stream));
 }
 
+int32_t tt_tower_fwd_supported(int64_t F, int64_t D, int64_t DI, int64_t hidden) {
+  return tower_fwd_supported(F, D, DI, hidden) ? 1 : 0;
+}
+int tt_tower_fwd(const tt_tower_problem* pr, int32_t count, int32_t* oob_flag, void* stream) {
+  TT_CHECK(pr != nullptr && count >= 1 && count <= 4, "tt_tower_fwd: 1..4 towers");
+  TowerProblem t[4];
+  for (int i = 0; i < count; ++i) {
+    const tt_tower_problem& q = pr[i];
+    t[i] = TowerProblem{(const long long*)q.ids, q.table, q.table_rows, q.feats, q.ld_feats, q.w0_bf16, q.ldw0, q.b0,
+                        q.w1_bf16, q.ldw1, q.b1, q.wt_bf16, q.ldwt, q.bt, q.feats_bf16, q.ld_feats16, q.h_bf16, q.ldh,
+                        q.x_bf16, q.ldx, q.emb_f32, q.ld_emb, q.emb_bf16, q.ld_emb16, q.rows, q.F, q.D, q.DI, q.hidden};
+  }
+  return tower_fwd(t, count, oob_flag, S(stream));
+}
+
 int64_t tt_inbatch_ce_workspace_bytes(int64_t B, int64_t N, int64_t d) {
   return (int64_t)inbatch_ce_workspace_bytes(B, N, d);
 }

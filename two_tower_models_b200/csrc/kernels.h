@@ -113,6 +113,37 @@ int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, l
                          const long long* ids, long long B, long long H, long long D, float* table_grad,
                          long long table_rows, cudaStream_t stream);
 
+// Fused tower forward (tower.cu): [table[ids] | MLP(feats)] Wt^T + bt for up to 4 towers of one shape per launch.
+struct TowerProblem {
+  const long long* ids;
+  const float* table;
+  long long table_rows;
+  const float* feats;
+  long long ld_feats;
+  const void* w0;  // bf16 [hidden, F]
+  long long ldw0;
+  const float* b0;
+  const void* w1;  // bf16 [D, hidden]
+  long long ldw1;
+  const float* b1;
+  const void* wt;  // bf16 [DI, 2D]
+  long long ldwt;
+  const float* bt;
+  void* feats16;  // out: bf16 [rows, F]
+  long long ld_feats16;
+  void* h16;  // out: bf16 [rows, hidden]
+  long long ldh;
+  void* x16;  // out: bf16 [rows, 2D] = [id_emb | feat_emb]
+  long long ldx;
+  float* emb32;  // out: fp32 [rows, DI]
+  long long ld_emb32;
+  void* emb16;  // out: bf16 [rows, DI]
+  long long ld_emb16;
+  long long rows, F, D, DI, hidden;
+};
+bool tower_fwd_supported(long long F, long long D, long long DI, long long hidden);
+int tower_fwd(const TowerProblem* problems, int n, int* oob_flag, cudaStream_t stream);
+
 int weighted_loss(const float* ce, const float* labels, long long ldl, const float* uvw, long long B, long long T,
                   float* loss, float* g, cudaStream_t stream);
 

@@ -328,16 +328,23 @@ class TowerFunction(torch.autograd.Function):
         w0_16 = packed.get(tag + ".w0", w0)
         w1_16 = packed.get(tag + ".w1", w1)
         wt_16 = packed.get(tag + ".wt", wt, segments=segs)
-        feats16 = cast_rows_bf16(feats)
         dense = (D8 == D) and (_r8(E) == E)
         X16 = (torch.empty if dense else torch.zeros)((B, KT), dtype=_BF16, device=feats.device)
-        gather_rows(table, ids, X16, 0)
-        H16 = _mlp_forward(feats16, F, w0_16, _f32c(b0), w1_16, _f32c(b1), D, out16=X16, out16_col=D8)
-        if E:
-            cast_rows_bf16(_f32c(extra), out=X16, col_offset=2 * D8)
         emb = torch.empty((B, DI), dtype=torch.float32, device=feats.device)
         emb16 = torch.empty((B, _r8(DI)), dtype=_BF16, device=feats.device)
-        gemm(X16, wt_16, B, DI, KT, bias=_f32c(bt), out32=emb, out16=emb16)
+        if tower_fused_supported(F, D, DI, w0.shape[0], E):
+            feats16 = torch.empty((B, F), dtype=_BF16, device=feats.device)
+            H16 = torch.empty((B, w0.shape[0]), dtype=_BF16, device=feats.device)
+            tower_forward_fused([dict(ids=ids, feats=feats, table=_f32c(table), w0_16=w0_16, w1_16=w1_16, wt_16=wt_16,
+                                      b0=_f32c(b0), b1=_f32c(b1), bt=_f32c(bt), feats16=feats16, H16=H16, X16=X16,
+                                      emb=emb, emb16=emb16, B=B, F=F, D=D, DI=DI, hid=w0.shape[0])])
+        else:
+            feats16 = cast_rows_bf16(feats)
+            gather_rows(table, ids, X16, 0)
+            H16 = _mlp_forward(feats16, F, w0_16, _f32c(b0), w1_16, _f32c(b1), D, out16=X16, out16_col=D8)
+            if E:
+                cast_rows_bf16(_f32c(extra), out=X16, col_offset=2 * D8)
+            gemm(X16, wt_16, B, DI, KT, bias=_f32c(bt), out32=emb, out16=emb16)
         ctx.save_for_backward(ids, feats16, H16, X16, w0_16, w1_16, wt_16)
         ctx.dims = (B, F, D, DI, E, D8, KT, table.shape[0])
         ctx.need_dfeats = feats.requires_grad
@@ -845,6 +852,34 @@ def gather_batched(items) -> None:
     _maybe_check_ids(items[0][0].device, "gather_rows")
 
 
+def tower_fused_supported(F: int, D: int, DI: int, hid: int, E: int) -> bool:
+    """Shapes the single-launch tower kernel takes (csrc/tower.cu); others use the per-layer launches."""
+    if os.environ.get("TT_B200_FUSED_TOWER", "1") != "1" or E != 0:
+        return False
+    return bool(_native.lib().tt_tower_fwd_supported(F, D, DI, hid))
+
+
+def tower_forward_fused(towers) -> None:
+    """towers: dicts with ids, feats (fp32), table, w0_16, w1_16, wt_16, b0, b1, bt and the outputs feats16, H16,
+    X16, emb, emb16: the whole forward of every tower in one launch (tt_tower_fwd)."""
+    arr = (_native.TowerProblem * len(towers))()
+    for t, d in zip(arr, towers):
+        t.ids, t.table, t.table_rows = d["ids"].data_ptr(), d["table"].data_ptr(), d["table"].shape[0]
+        t.feats, t.ld_feats = d["feats"].data_ptr(), d["feats"].stride(0)
+        t.w0_bf16, t.ldw0, t.b0 = d["w0_16"].data_ptr(), d["w0_16"].stride(0), d["b0"].data_ptr()
+        t.w1_bf16, t.ldw1, t.b1 = d["w1_16"].data_ptr(), d["w1_16"].stride(0), d["b1"].data_ptr()
+        t.wt_bf16, t.ldwt, t.bt = d["wt_16"].data_ptr(), d["wt_16"].stride(0), d["bt"].data_ptr()
+        t.feats_bf16, t.ld_feats16 = d["feats16"].data_ptr(), d["feats16"].stride(0)
+        t.h_bf16, t.ldh = d["H16"].data_ptr(), d["H16"].stride(0)
+        t.x_bf16, t.ldx = d["X16"].data_ptr(), d["X16"].stride(0)
+        t.emb_f32, t.ld_emb = d["emb"].data_ptr(), d["emb"].stride(0)
+        t.emb_bf16, t.ld_emb16 = d["emb16"].data_ptr(), d["emb16"].stride(0)
+        t.rows, t.F, t.D, t.DI, t.hidden = d["B"], d["F"], d["D"], d["DI"], d["hid"]
+    flag = _oob_flag(towers[0]["feats"].device)
+    _native.check(_native.lib().tt_tower_fwd(arr, len(towers), flag.data_ptr(), _stream()), "tower_fwd")
+    _maybe_check_ids(towers[0]["feats"].device, "gather_rows")
+
+
 _aux_streams = {}
 
 
@@ -911,12 +946,17 @@ class TowerSetFunction(torch.autograd.Function):
                 d["w1_16"] = _stage_weight(packed, tag + ".w1", w1, casts)
                 d["wt_16"] = _stage_weight(packed, tag + ".wt", wt, casts, segments=segs)
                 d["feats16"] = torch.empty((B, _r8(F)), dtype=_BF16, device=dev)
-                casts.append((feats, 0, F, d["feats16"], 0, _r8(F)))
+                d["fused"] = tower_fused_supported(F, D, DI, hid, E)
+                if d["fused"]:
+                    d["feats"], d["table"] = feats, _f32c(table)
+                else:
+                    casts.append((feats, 0, F, d["feats16"], 0, _r8(F)))
                 dense = (D8 == D) and (_r8(E) == E)
                 d["X16"] = (torch.empty if dense else torch.zeros)((B, KT), dtype=_BF16, device=dev)
                 if E:
                     casts.append((_f32c(extra), 0, E, d["X16"], 2 * D8, E))
-                gathers.append((_f32c(table), ids, d["X16"], 0))
+                if not d["fused"]:
+                    gathers.append((_f32c(table), ids, d["X16"], 0))
                 d["H16"] = torch.empty((B, hid), dtype=_BF16, device=dev)
                 d["emb"] = torch.empty((B, DI), dtype=torch.float32, device=dev)
                 d["emb16"] = torch.empty((B, _r8(DI)), dtype=_BF16, device=dev)
@@ -934,14 +974,26 @@ class TowerSetFunction(torch.autograd.Function):
                         d["dtable"] = torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=cur.device)
                     ev = torch.cuda.Event()
                     ev.record(aux)
-            cast_batched(casts)
-            gather_batched(gathers)
-            gemm_batched([dict(A=d["feats16"], B=d["w0_16"], M=d["B"], N=d["hid"], K=d["F"], bias=d["b0"], relu=True,
-                               out16=d["H16"]) for d in tw])
-            gemm_batched([dict(A=d["H16"], B=d["w1_16"], M=d["B"], N=d["D"], K=d["hid"], bias=d["b1"],
-                               out16=d["X16"][:, d["D8"]:]) for d in tw])
-            gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
-                               out16=d["emb16"]) for d in tw])
+            if casts:
+                cast_batched(casts)
+            fused = [d for d in tw if d["fused"]]
+            layered = [d for d in tw if not d["fused"]]
+            by_shape = {}
+            for d in fused:  # one launch for up to 4 towers of the same shape
+                by_shape.setdefault((d["F"], d["D"], d["DI"]), []).append(d)
+            for group in by_shape.values():
+                for i0 in range(0, len(group), 4):
+                    tower_forward_fused(group[i0:i0 + 4])
+            for d in fused:  # inputs are not needed after the launch (backward uses the bf16 copies)
+                d.pop("feats"), d.pop("table")
+            if layered:
+                gather_batched(gathers)
+                gemm_batched([dict(A=d["feats16"], B=d["w0_16"], M=d["B"], N=d["hid"], K=d["F"], bias=d["b0"], relu=True,
+                                   out16=d["H16"]) for d in layered])
+                gemm_batched([dict(A=d["H16"], B=d["w1_16"], M=d["B"], N=d["D"], K=d["hid"], bias=d["b1"],
+                                   out16=d["X16"][:, d["D8"]:]) for d in layered])
+                gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
+                                   out16=d["emb16"]) for d in layered])
             if zero_jobs:  # join the side stream again (the fills are long done: they ran beside the kernels above)
                 cur.wait_event(ev)
                 for d in zero_jobs:
