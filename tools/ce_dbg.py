@@ -12,7 +12,7 @@ U = (torch.randn(M, d, device=dev) * 0.4).to(torch.bfloat16)
 V = (torch.randn(M, d, device=dev) * 0.4).to(torch.bfloat16)
 tr = torch.zeros(4 * 64 * 2, dtype=torch.int64, device=dev)
 os.environ["TT_CE_TRACE"] = str(tr.data_ptr())
-for dbg in [0, 1, 4, 32, 33]:
+for dbg in [0, 1, 32, 33, 36]:
     os.environ["TT_CE_DBG"] = str(dbg | 16)
     for _ in range(20):
         ops.inbatch_ce_forward_raw(U, V, M, M, d, 0)

@@ -207,7 +207,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
 #ifdef TT_CE_BRINGUP
       if (a.dbg & 32) {  // synthetic scores instead of the TMEM load
 #pragma unroll
-        for (int i = 0; i < CW; ++i) x[i] = (float)(int)(tt * 7 + i) * 0.01f - 3.f;
+        for (int i = 0; i < CW; ++i) x[i] = fmaf(__uint_as_float(tt), 0.001f * (float)(i + 1), -0.05f * (float)i);
         return;
       }
 #endif
@@ -328,33 +328,53 @@ struct DiagOperands {
   long long rows_per_part, ldv, target_offset;
   int d;
 };
-__device__ __forceinline__ float positive_logit(const DiagOperands& o, long long row) {
-  const long long t = row + o.target_offset;
-  const long long p = t / o.rows_per_part;
-  const bf16* u = o.U + row * o.ldu;
-  const bf16* v = o.Vp[p] + (t - p * o.rows_per_part) * o.ldv;
-  float acc0 = 0.f, acc1 = 0.f;
-  int k = 0;
-  for (; k + 8 <= o.d; k += 8) {  // rows are 16-byte aligned (operand pitch is a multiple of 8 elements)
-    const uint4 a4 = *reinterpret_cast<const uint4*>(u + k);
-    const uint4 b4 = *reinterpret_cast<const uint4*>(v + k);
-    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+// Block-cooperative version for 256-thread blocks with one row per thread: every warp computes the logits of its 32
+// rows with 16 (d <= 128) or 32 lanes per row, so the 16-byte loads of a row are coalesced and all of a lane's loads
+// are in flight together (one thread walking its own row pays one L2 round trip per 16 bytes).  Returns the logit of
+// the calling thread's row (row0 + threadIdx.x).
+static constexpr int COMBINE_RB = 64;  // rows per 256-thread block of the merge kernels
+// RB = rows per 256-thread block (the first RB threads own one row each afterwards).
+template <int RB>
+__device__ __forceinline__ float positive_logit_block(const DiagOperands& o, long long row0, int B, float* sdiag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = (o.d + 7) / 8;            // 16-byte chunks per row (<= 32)
+  const int lpr = chunks <= 16 ? 16 : 32;      // lanes per row
+  const int rpi = 32 / lpr;                    // rows per warp iteration
+  const int sub = lane / lpr, c = lane % lpr;
+  constexpr int RW = RB / 8;                   // rows per warp
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
-      acc0 = fmaf(fa.x, fb.x, acc0);
-      acc1 = fmaf(fa.y, fb.y, acc1);
+  for (int i = 0; i < RW; ++i) {
+    if (i * rpi >= RW) break;
+    const int lr = warp * RW + i * rpi + sub;  // row inside the block
+    const long long row = row0 + lr;
+    float acc = 0.f;
+    if (row < B && c < chunks) {
+      const long long t = row + o.target_offset;
+      const long long p = t / o.rows_per_part;
+      const uint4 a4 = *reinterpret_cast<const uint4*>(o.U + row * o.ldu + c * 8);
+      const uint4 b4 = *reinterpret_cast<const uint4*>(o.Vp[p] + (t - p * o.rows_per_part) * o.ldv + c * 8);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __bfloat1622float2(a2[k]), fb = __bfloat1622float2(b2[k]);
+        if (c * 8 + 2 * k < o.d) acc = fmaf(fa.x, fb.x, acc);
+        if (c * 8 + 2 * k + 1 < o.d) acc = fmaf(fa.y, fb.y, acc);
+      }
     }
+    for (int off = lpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (c == 0) sdiag[lr] = acc;
   }
-  for (; k < o.d; ++k) acc0 = fmaf(__bfloat162float(u[k]), __bfloat162float(v[k]), acc0);
-  return acc0 + acc1;
+  __syncthreads();
+  return sdiag[threadIdx.x % RB];
 }
 
 __global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, const float* part_m, const float* part_s,
                                   const DiagOperands dg, float* ce, float* lse) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= B) return;
+  __shared__ float sdiag[COMBINE_RB];
+  const long long row = (long long)blockIdx.x * COMBINE_RB + threadIdx.x;
+  const float pos = positive_logit_block<COMBINE_RB>(dg, (long long)blockIdx.x * COMBINE_RB, B, sdiag);
+  if (threadIdx.x >= COMBINE_RB || row >= B) return;
   const long long r = row / 128;
   const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
   float M = -INFINITY;
@@ -368,7 +388,7 @@ __global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, co
     }
   const float l = (M + log2f(S)) * LN2;
   lse[row] = l;
-  ce[row] = l - positive_logit(dg, row);
+  ce[row] = l - pos;
 }
 
 // combine + value-weighted mean in ONE launch (identity debias hook, reference :322-343).  Every block merges the
@@ -390,11 +410,13 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
                        const float* __restrict__ uvw, int TL, float inv_rows, float* __restrict__ loss,
                        float* __restrict__ g, float* __restrict__ g_norm, LossSync* sync) {
   __shared__ float red_m[8], red_s[8];
+  __shared__ float sdiag[COMBINE_RB];
   __shared__ unsigned int last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row = (long long)blockIdx.x * blockDim.x + tid;
+  const long long row = (long long)blockIdx.x * COMBINE_RB + tid;
+  const float pos = positive_logit_block<COMBINE_RB>(dg, (long long)blockIdx.x * COMBINE_RB, B, sdiag);
   float nuv = 0.f, cw = 0.f;
-  if (row < B) {
+  if (tid < COMBINE_RB && row < B) {
     const long long r = row / 128;
     const int first = (int)((r * CT) / T), last_slot = (int)(((r + 1) * CT - 1) / T);
     float M = -INFINITY;
@@ -407,7 +429,7 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
         S += part_s[o] * exp2f(part_m[o] - M);
       }
     const float l = (M + log2f(S)) * LN2;
-    const float c = l - positive_logit(dg, row);
+    const float c = l - pos;
     lse[row] = l;
     ce[row] = c;
     for (int t = 0; t < TL; ++t) nuv = fmaf(labels[row * ldl + t], uvw[t], nuv);
@@ -556,7 +578,7 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
   else if (DP == 128) rc = launch_ce_fwd<128>(tx, ty, a, s.grid, stream);
   else rc = launch_ce_fwd<256>(tx, ty, a, s.grid, stream);
   if (rc) return rc;
-  const long long loss_blocks = (B + 255) / 256;
+  const long long loss_blocks = (B + COMBINE_RB - 1) / COMBINE_RB;
   if (labels != nullptr && loss_blocks <= LOSS_MAX_BLOCKS) {
     TT_CHECK(TL > 0 && ldl >= TL && uvw && loss && g && g_norm, "inbatch_ce_loss_fwd: bad label arguments");
     KernelSpan span("ce_combine_loss_kernel", stream);
@@ -569,7 +591,7 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
   }
   {
     KernelSpan span("ce_combine_kernel", stream);
-    ce_combine_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, dgo, ce, lse);
+    ce_combine_kernel<<<(unsigned)((B + COMBINE_RB - 1) / COMBINE_RB), 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, dgo, ce, lse);
     TT_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -598,40 +620,62 @@ struct ReduceJob {
   float* colsum;  // [d] or null; caller initialises
   int blocks;
 };
+// Persistent blocks stride over groups of (256 / (DP/4)) rows; a thread owns 4 columns, adds the slot partials with
+// 16-byte loads, writes fp32 / bf16 results with vector stores and keeps the column sums of everything it has seen in
+// registers (one shared-memory fold and one atomic per column per BLOCK at the end).  Launched with a few blocks per SM:
+// the first version (one block per 256 outputs, scalar stores, an atomic per column per block) was instruction bound.
 __global__ void __launch_bounds__(256)
 ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
   __shared__ float red[1024];  // [rows of the block][DP columns]
-  const bool second = (int)blockIdx.x >= j0.blocks;
-  const ReduceJob& j = second ? j1 : j0;
-  const long long idx = (long long)(blockIdx.x - (second ? j0.blocks : 0)) * blockDim.x + threadIdx.x;
-  const int cpr = DP / 4;
-  const long long row = idx / cpr;
-  const int c = (int)(idx % cpr) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < j.rows) {
-    const long long r = row / 128;
-    const int first = (int)((r * j.CT) / j.T), last = (int)(((r + 1) * j.CT - 1) / j.T);
-    for (int sl = 0; sl <= last - first; ++sl) {
-      const float4 p = *reinterpret_cast<const float4*>(j.partial + (long long)sl * j.slot_stride + row * DP + c);
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
-    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
-    for (int i = 0; i < 4; ++i) {
-      if (c + i < j.d) {
-        if (j.out32) j.out32[row * j.ld32 + c + i] = vals[i];
-        if (j.out16) j.out16[row * j.ld16 + c + i] = __float2bfloat16(vals[i]);
+  const int cpr = DP / 4, rpb = 256 / cpr;
+  const int ry = threadIdx.x / cpr, c = (threadIdx.x % cpr) * 4;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const ReduceJob& j = which ? j1 : j0;
+    if (j.blocks == 0) continue;
+    const int T = (int)j.T, CT = j.CT;
+    const bool vec32 = j.out32 != nullptr && (j.ld32 % 4) == 0 && c + 3 < j.d;
+    const bool vec16 = j.out16 != nullptr && (j.ld16 % 4) == 0 && c + 3 < j.d;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int groups = (j.rows + rpb - 1) / rpb;
+    for (int gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+      const int row = gi * rpb + ry;
+      if (row >= j.rows) continue;
+      const int r = row >> 7;
+      const int nsl = (int)((((long long)r + 1) * CT - 1) / T) - (int)(((long long)r * CT) / T);  // last - first slot
+      const float* src = j.partial + (long long)row * DP + c;
+      float4 acc = *reinterpret_cast<const float4*>(src);
+      for (int sl = 1; sl <= nsl; ++sl) {
+        const float4 p = *reinterpret_cast<const float4*>(src + (long long)sl * j.slot_stride);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
       }
+      if (vec32) {
+        *reinterpret_cast<float4*>(j.out32 + (long long)row * j.ld32 + c) = acc;
+      } else if (j.out32 != nullptr) {
+        const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (int i = 0; i < 4; ++i)
+          if (c + i < j.d) j.out32[(long long)row * j.ld32 + c + i] = vals[i];
+      }
+      if (vec16) {
+        *reinterpret_cast<uint2*>(j.out16 + (long long)row * j.ld16 + c) =
+            make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+      } else if (j.out16 != nullptr) {
+        const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (int i = 0; i < 4; ++i)
+          if (c + i < j.d) j.out16[(long long)row * j.ld16 + c + i] = __float2bfloat16(vals[i]);
+      }
+      cs.x += acc.x; cs.y += acc.y; cs.z += acc.z; cs.w += acc.w;
     }
-  }
-  if (j.colsum != nullptr && cpr <= 32) {  // block = (256 / cpr) rows x cpr column groups
-    const int rpb = 256 / cpr, ry = threadIdx.x / cpr, cx = threadIdx.x % cpr;
-    float* rr = red + ry * DP + cx * 4;
-    rr[0] = acc.x; rr[1] = acc.y; rr[2] = acc.z; rr[3] = acc.w;
-    __syncthreads();
-    if (threadIdx.x < DP && threadIdx.x < j.d) {
-      float t = 0.f;
-      for (int i = 0; i < rpb; ++i) t += red[i * DP + threadIdx.x];
-      atomicAdd(j.colsum + threadIdx.x, t);
+    if (j.colsum != nullptr && cpr <= 32) {  // block = rpb rows x cpr column groups
+      __syncthreads();
+      float* rr = red + ry * DP + c;
+      rr[0] = cs.x; rr[1] = cs.y; rr[2] = cs.z; rr[3] = cs.w;
+      __syncthreads();
+      if ((int)threadIdx.x < DP && (int)threadIdx.x < j.d) {
+        float t = 0.f;
+        for (int i = 0; i < rpb; ++i) t += red[i * DP + threadIdx.x];
+        atomicAdd(j.colsum + threadIdx.x, t);
+      }
     }
   }
 }
@@ -718,7 +762,8 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
   if (ja.blocks + jb.blocks == 0) return 0;
   if (DP > 128) { ja.colsum = nullptr; jb.colsum = nullptr; }  // handled by the caller (tt_colsum) for wide rows
   KernelSpan span("ce_bwd_reduce_kernel", stream);
-  ce_bwd_reduce_kernel<<<(unsigned)(ja.blocks + jb.blocks), 256, 0, stream>>>(ja, jb, DP);
+  const int want = ja.blocks + jb.blocks, cap = 4 * num_sms();
+  ce_bwd_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(ja, jb, DP);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -883,12 +883,15 @@ def tower_forward_fused(towers) -> None:
 _aux_streams = {}
 
 
-def _aux_stream(device) -> "torch.cuda.Stream":
-    st = _aux_streams.get(device)
+def _aux_stream(device, idx: int = 0) -> "torch.cuda.Stream":
+    st = _aux_streams.get((device, idx))
     if st is None:
         st = torch.cuda.Stream(device=device)
-        _aux_streams[device] = st
+        _aux_streams[(device, idx)] = st
     return st
+
+
+_PARALLEL_BACKWARD = os.environ.get("TT_B200_PARALLEL_BACKWARD", "1") == "1"
 
 
 def _stage_weight(packed: PackedWeights, key, param, casts, segments=None) -> torch.Tensor:
@@ -1037,19 +1040,45 @@ class TowerSetFunction(torch.autograd.Function):
                 d["dbt"] = d["demb_colsum"]  # already reduced (fp32) by the kernel that produced demb
             else:
                 colsum(d["demb"], d["DI"], out=d["dbt"])  # fp32 source: analytically-zero sums stay at fp32 noise
+        # The gradient kernels are small and latency-bound, and only dX -> dH -> dW0 is a true chain: the weight
+        # gradients that need no dX (tower Linear) or only dX (MLP layer 1) and the embedding scatter-adds run on side
+        # streams beside it (parallel branches of the captured graph), joined before the results are handed back.
+        cur = torch.cuda.current_stream(dev)
+        par = _PARALLEL_BACKWARD and all(d["row_exchange"] is None for d in tw)  # collectives stay on one stream
+        s1, s2 = (_aux_stream(dev, 1), _aux_stream(dev, 2)) if par else (cur, cur)
+        for d in tw:  # buffers are allocated on the main stream; zero-filled beside the forward kernels when possible
+            pre = d.pop("dtable", None)
+            d["dtable_buf"] = pre if pre is not None else torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=dev)
+        if par:
+            s1.wait_stream(cur)
+        with torch.cuda.stream(s1):  # dWt = demb^T X (split-K over the batch)
+            gemm_batched([dict(A=d["demb16"], B=d["X16"], M=d["DI"], N=d["KT"], K=d["B"], a_mn=True, b_mn=True,
+                               out32=d["dWt_p"], accumulate=True) for d in tw])
         # dX = demb Wt (+ fp32 column sums = bias gradient of the second MLP layer)
         gemm_batched([dict(A=d["demb16"], B=d["wt_16"], M=d["B"], N=d["KT"], K=d["DI"], b_mn=True, out16=d["dX16"],
                            colsum=d["dXsum"]) for d in tw])
-        # weight gradients of the tower Linear and of MLP layer 1 (split-K over the batch)
-        gemm_batched([dict(A=d["demb16"], B=d["X16"], M=d["DI"], N=d["KT"], K=d["B"], a_mn=True, b_mn=True,
-                           out32=d["dWt_p"], accumulate=True) for d in tw] +
-                     [dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
-                           out32=d["dW1"], accumulate=True) for d in tw])
+        if par:
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+        with torch.cuda.stream(s1):  # dW1 = dFe^T H
+            gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
+                               out32=d["dW1"], accumulate=True) for d in tw])
+        with torch.cuda.stream(s2):  # id embeddings (dense gradient, duplicates accumulate)
+            for d in tw:
+                pre = d.pop("dtable_buf")
+                if d["row_exchange"] is not None:
+                    ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :d["D8"]].contiguous())
+                    d["dtable_out"] = scatter_add_rows(rows_all, ids_all, d["D"], d["table_rows"], col_offset=0, grad=pre)
+                else:
+                    d["dtable_out"] = scatter_add_rows(d["dX16"], d["ids"], d["D"], d["table_rows"], col_offset=0, grad=pre)
         # dH = (dFe W1) masked by ReLU (+ column sums = bias gradient of layer 0)
         gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["w1_16"], M=d["B"], N=d["hid"], K=d["D"], b_mn=True,
                            relu_mask=d["H16"], out16=d["dH16"], colsum=d["db0"]) for d in tw])
         gemm_batched([dict(A=d["dH16"], B=d["feats16"], M=d["hid"], N=d["F"], K=d["B"], a_mn=True, b_mn=True,
                            out32=d["dW0"], accumulate=True) for d in tw])
+        if par:
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
         grads = []
         for d in tw:
             D, D8, E, KT = d["D"], d["D8"], d["E"], d["KT"]
@@ -1058,18 +1087,21 @@ class TowerSetFunction(torch.autograd.Function):
             else:
                 parts = [d["dWt_p"][:, :D], d["dWt_p"][:, D8:D8 + D]] + ([d["dWt_p"][:, 2 * D8:2 * D8 + E]] if E else [])
                 dWt = torch.cat(parts, dim=1)
-            pre = d.pop("dtable", None)  # zero-filled on the side stream during forward (first backward only)
-            if d["row_exchange"] is not None:
-                ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :D8].contiguous())
-                dtable = scatter_add_rows(rows_all, ids_all, D, d["table_rows"], col_offset=0, grad=pre)
-            else:
-                dtable = scatter_add_rows(d["dX16"], d["ids"], D, d["table_rows"], col_offset=0, grad=pre)
+            dtable = d.pop("dtable_out")
             dfeats = None
             if d["need_dfeats"]:
                 dfeats = torch.empty((d["B"], d["F"]), dtype=torch.float32, device=dev)
                 gemm(d["dH16"], d["w0_16"], d["B"], d["F"], d["hid"], b_mn=True, out32=dfeats)
             dextra = d["dX16"][:, 2 * D8:2 * D8 + E].float() if d["has_extra"] else None
-            grads += [None, dfeats, dextra, dtable, d["dW0"], d["db0"], d["dW1"], d["dXsum"][D8:D8 + D], dWt, d["dbt"]]
+            db1 = d["dXsum"][D8:D8 + D]
+            # no reference to a gradient may stay behind in ctx: AccumulateGrad adopts a fresh gradient in place only
+            # when it holds the last reference, otherwise it clones it (one copy launch per parameter)
+            dW0, db0, dW1, dbt = d.pop("dW0"), d.pop("db0"), d.pop("dW1"), d.pop("dbt")
+            for k in ("dWt_p", "dXsum", "demb", "demb16", "demb_colsum", "dX16", "dH16"):
+                d.pop(k, None)
+            grads += [None, dfeats, dextra, dtable, dW0, db0, dW1, db1, dWt, dbt]
+            del dW0, db0, dW1, dbt, db1, dWt, dtable
+        del arena
         return (None, None, *grads)
 
 
