@@ -30,7 +30,7 @@ struct Cfg2 {
   static constexpr int X_BYTES = 128 * DP * 2;
   static constexpr int Y_BYTES = BN * DP * 2;
   static constexpr int STAGES = DP == 64 ? 8 : (DP == 128 ? 6 : 4);
-  static constexpr int COLSTAT_BYTES = BN * 8;
+  static constexpr int COLSTAT_BYTES = BN * 8;  // (g, lse) per column of the current tile
   static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + COLSTAT_BYTES + 1024 + 256;
   static constexpr int ACC_COL = NS * BN;
   static constexpr int E_COL = ACC_COL + DP;
@@ -248,18 +248,24 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         rl = valid ? a.lse[row] * LOG2E : 0.f;
       }
       const long long tgt = row + a.diag_shift;
+      // column statistics (g, lse) of the tile's columns live in shared memory: the loads for tile j + 1 are issued
+      // before tile j is transformed and are written afterwards, so their L2 round trip hides behind the tile instead
+      // of stalling every tile.
+      auto colstat_load = [&](int jj) -> float2 {
+        const long long col = (long long)jj * BN + e * (BN / 2) + wg_tid;
+        const bool cv = wg_tid < BN / 2 && col < a.YR;
+        return make_float2(cv ? a.g[col] * gs : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
+      };
+      if (COLSTATS) {
+        const float2 cs0 = colstat_load(j0);
+        if (wg_tid < BN / 2) scol[e * (BN / 2) + wg_tid] = cs0;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+      }
       for (int j = j0; j < j1; ++j, ++t) {
         const uint32_t buf = t % NS;
-        if (COLSTATS) {
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
-          if (wg_tid < BN / 2) {
-            const int cidx = e * (BN / 2) + wg_tid;
-            const long long col = (long long)j * BN + cidx;
-            const bool cv = col < a.YR;
-            scol[cidx] = make_float2(cv ? a.g[col] * gs : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
-        }
+        const float2* sc = scol;
+        float2 cs_next = make_float2(0.f, 0.f);
+        if (COLSTATS && j + 1 < j1) cs_next = colstat_load(j + 1);
         mbar_wait(&s_full[buf], (t / NS) & 1);
         tc_fence_after();
         if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 0);
@@ -277,14 +283,14 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {  // (g, lse) of two columns per 16-byte broadcast load
-              const float4 cc4 = *reinterpret_cast<const float4*>(&scol[c * 32 + i]);
+              const float4 cc4 = *reinterpret_cast<const float4*>(&sc[c * 32 + i]);
               v[i] = cc4.x * ex2f(fmaf(v[i], LOG2E, -cc4.y));
               v[i + 1] = cc4.z * ex2f(fmaf(v[i + 1], LOG2E, -cc4.w));
             }
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (n0 + i == tgt) v[i] -= scol[c * 32 + i].x;
+                if (n0 + i == tgt) v[i] -= sc[c * 32 + i].x;
             }
           }
 #pragma unroll
@@ -319,6 +325,11 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         if (lane == 0) {
           mbar_arrive(&s_empty[buf]);
           mbar_arrive(&e_full[e]);
+        }
+        if (COLSTATS && j + 1 < j1) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");  // every thread of the group is done with tile j's
+          if (wg_tid < BN / 2) scol[e * (BN / 2) + wg_tid] = cs_next;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
         }
         if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 1);
       }
