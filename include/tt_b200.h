@@ -204,6 +204,23 @@ int tt_inbatch_ce_bwd_scaled(const void* U_bf16, int64_t ldu, const void* V_bf16
                              float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
                              float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- optimizer (the adjacent step of the training loop) --------------------------- */
+
+/* One launch of torch.optim.Adam's update (amsgrad off; reference train/train.py:179, :123-125) over `count` <= 32
+ * fp32 tensors: exp_avg += (grad - exp_avg)(1 - beta1); exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) grad^2;
+ * param -= lr / (1 - beta1^t) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps), t = *step_dev + 1;
+ * weight_decay != 0 adds weight_decay * param to grad first.  *step_dev (int64, device) is incremented by the launch,
+ * ticket_dev is a zero-initialised uint32 scratch word owned by the optimizer (both make CUDA-graph replay work). */
+typedef struct tt_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} tt_adam_tensor;
+int tt_adam_step(const tt_adam_tensor* tensors, int32_t count, double lr, double beta1, double beta2, float eps,
+                 float weight_decay, int64_t* step_dev, uint32_t* ticket_dev, void* stream);
+
 /* ---- brute-force MIPS ------------------------------------------------------------------------ */
 
 /* Scratch bytes needed by tt_mips_topk for this shape on the current device. */

@@ -62,6 +62,12 @@ __all__ = [
     "history_user_embedding",
     "history_train_forward",
     "history_train_forward_with_grads",
+    "DEBIAS_HOOKS",
+    "debias_position",
+    "debias_user",
+    "debias_both",
+    "debias_train_forward",
+    "debias_train_forward_with_grads",
     "mips_topk",
     "mips_forward",
 ]
@@ -301,6 +307,48 @@ def history_train_forward(params, user_value_weights, batch, heads: int, pe: Opt
 
 def history_train_forward_with_grads(params, user_value_weights, batch, heads, pe):
     return _with_grads(history_train_forward, params, user_value_weights, batch, heads, pe)
+
+
+# --------------------------------------------------------------------------------------
+# debias_net_user_value overrides  
+# --------------------------------------------------------------------------------------
+def debias_position(params, nuv: Tensor, position: Tensor, u: Tensor) -> Tuple[Tensor, Tensor]:
+    """src/two_tower_with_position_debiased_weights.py:76-113."""
+    est = params["position_bias_net_user_value.weight"][position][:, 0]
+    return nuv / torch.clamp(est, min=1e-3), torch.sum((est - nuv) ** 2)
+
+
+def debias_user(params, nuv: Tensor, position: Tensor, u: Tensor) -> Tuple[Tensor, Tensor]:
+    """src/two_tower_with_user_debiased_weights.py:100-135 (clamp at 1e-1 before the squared error)."""
+    w, b = params["user_debias_net_user_value.0.weight"], params["user_debias_net_user_value.0.bias"]
+    est = torch.clamp((u @ w.t() + b)[:, 0], min=1e-1)
+    return nuv / est, torch.sum((est - nuv) ** 2)
+
+
+def debias_both(params, nuv: Tensor, position: Tensor, u: Tensor) -> Tuple[Tensor, Tensor]:
+    """src/two_tower_with_debiasing.py:77-129; the position term is a sum over all B x B (estimate_i, target_j)
+    pairs because the reference's mse_loss broadcasts [B,1] against [B] (:110)."""
+    pos = params["position_bias_net_user_value.weight"][position]  # [B,1]
+    w, b = params["user_debias_net_user_value.0.weight"], params["user_debias_net_user_value.0.bias"]
+    est = (torch.cat([u, pos], dim=-1) @ w.t() + b)[:, 0]
+    loss = torch.sum((est - nuv) ** 2) + torch.sum((pos - nuv[None, :]) ** 2)
+    return nuv / torch.clamp(est, min=1e-3), loss
+
+
+DEBIAS_HOOKS = {"position": debias_position, "user": debias_user, "both": debias_both}
+
+
+def debias_train_forward(params, user_value_weights, batch, heads: int, pe: Optional[Tensor], kind: str) -> Tensor:
+    """train_forward of the history model with a debias hook between the label weights and the clamp (:322-346)."""
+    u = history_user_embedding(params, batch["user_id"], batch["user_features"], batch["user_history"], heads, pe)
+    v = base_item_embedding(params, batch["item_id"], batch["item_features"])
+    ce, _ = inbatch_ce(u, v)
+    nuv, extra = DEBIAS_HOOKS[kind](params, net_user_value(batch["labels"], user_value_weights), batch["position"], u)
+    return weighted_loss(ce, nuv) + extra
+
+
+def debias_train_forward_with_grads(params, user_value_weights, batch, heads, pe, kind):
+    return _with_grads(debias_train_forward, params, user_value_weights, batch, heads, pe, kind)
 
 
 # --------------------------------------------------------------------------------------

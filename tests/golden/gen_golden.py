@@ -104,6 +104,34 @@ def gen_history(name, seed, B, DU, DI, IU, II, H, uhash, ihash, uvw):
     _save(name, d)
 
 
+def gen_debias(name, kind, seed, B, DU, DI, IU, II, H, uhash, ihash, uvw):
+    """The three debias_net_user_value subclasses (position / user / both), loss and every gradient."""
+    import warnings
+
+    from src.two_tower_with_debiasing import TwoTowerWithDebiasing
+    from src.two_tower_with_position_debiased_weights import TwoTowerWithPositionDebiasedWeights
+    from src.two_tower_with_user_debiased_weights import TwoTowerWithUserDebiasedWeights
+
+    cls = {"position": TwoTowerWithPositionDebiasedWeights, "user": TwoTowerWithUserDebiasedWeights,
+           "both": TwoTowerWithDebiasing}[kind]
+    torch.manual_seed(seed)
+    mips = BaselineMIPSModule(corpus_size=129, embedding_dim=DI)
+    model = cls(
+        num_items=5, user_id_hash_size=uhash, user_id_embedding_dim=DU, user_features_size=IU,
+        user_history_seqlen=H, item_id_hash_size=ihash, item_id_embedding_dim=DI, item_features_size=II,
+        user_value_weights=uvw, mips_module=mips,
+    )
+    g = torch.Generator().manual_seed(seed + 1000)
+    batch = _batch(g, B, IU, II, H, uhash, ihash, len(uvw))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # the reference's own broadcasting UserWarning (two_tower_with_debiasing.py:110)
+        d = _run_train(model, batch)
+    d["attr:positional_embeddings"] = model.user_history_encoder.positional_embeddings
+    d["attr:heads"] = model.user_history_encoder.num_attention_heads
+    d["attr:kind"] = np.array(kind)
+    _save(name, d)
+
+
 def gen_encoder_kats():
     """The reference's two known-answer tests (tests/test_user_history_enc.py:48-124), seed 42."""
     d = {}
@@ -162,6 +190,9 @@ if __name__ == "__main__":
     # a scaled-down config-1 (d=64, F=64), single task
     gen_base("base_c1small.npz", 1, B=96, DU=64, DI=64, IU=64, II=64, uhash=300, ihash=300, uvw=[1.0])
     gen_history("hist_small.npz", 2, B=12, DU=24, DI=32, IU=16, II=20, H=10, uhash=50, ihash=60, uvw=[1.0, 0.5])
+    for i, kind in enumerate(("position", "user", "both")):
+        gen_debias(f"debias_{kind}.npz", kind, 10 + i, B=16, DU=24, DI=32, IU=16, II=20, H=8, uhash=50, ihash=60,
+                   uvw=[1.0, 0.5])
     gen_encoder_kats()
     gen_encoder("encoder_l2.npz", 3, B=6, H=20, D=64, heads=4, L=2)
     gen_mips()

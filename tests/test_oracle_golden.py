@@ -1,5 +1,6 @@
 """Pin the oracle: replay every golden vector produced by the reference (tests/golden/gen_golden.py)
 and the reference's own two known-answer tests (reference tests/test_user_history_enc.py:48-124)."""
+import pytest
 import torch
 
 import oracle
@@ -107,3 +108,17 @@ def test_mips_randn_and_exact_grid():
     # gathered scores are self-consistent
     full = g["grid:q"] @ g["grid:corpus"].t()
     assert torch.equal(torch.gather(full, 1, idx2), sc2)
+
+
+@pytest.mark.parametrize("kind", ["position", "user", "both"])
+def test_debias_hook_models(kind):
+    """The three debias_net_user_value subclasses: oracle restatement of the hooks vs the reference's loss and every
+    parameter gradient (tests/golden/debias_*.npz, produced by the unmodified reference)."""
+    g = load_golden(f"debias_{kind}.npz")
+    p, batch, grads = section(g, "p:"), section(g, "in:"), section(g, "grad:")
+    uvw, heads, pe = g["attr:user_value_weights"], int(g["attr:heads"]), g["attr:positional_embeddings"]
+    loss, og = oracle.debias_train_forward_with_grads(p, uvw, batch, heads, pe, kind)
+    assert abs(float(loss) - float(g["out:loss"])) <= 5e-6 * abs(float(g["out:loss"])) + 1e-6
+    assert set(og) == set(grads)
+    for k in grads:
+        assert_close_fro(og[k], grads[k], rtol=5e-5, atol=5e-8, what=k)

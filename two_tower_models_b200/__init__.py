@@ -7,12 +7,22 @@ include/tt_b200.h (libtt_b200.so).  CUDA only - there is no CPU fallback.
 from . import _native, ops  # noqa: F401
 from .history import UserHistoryEncoder  # noqa: F401
 from .mips import BaselineMIPSModule  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .towers import TwoTowerBaseRetrieval, TwoTowerWithUserHistoryEncoder  # noqa: F401
+from .debias import (  # noqa: F401
+    TwoTowerWithDebiasing,
+    TwoTowerWithPositionDebiasedWeights,
+    TwoTowerWithUserDebiasedWeights,
+)
 
 __all__ = [
     "ops",
     "BaselineMIPSModule",
+    "FusedAdam",
     "TwoTowerBaseRetrieval",
     "TwoTowerWithUserHistoryEncoder",
+    "TwoTowerWithPositionDebiasedWeights",
+    "TwoTowerWithUserDebiasedWeights",
+    "TwoTowerWithDebiasing",
     "UserHistoryEncoder",
 ]

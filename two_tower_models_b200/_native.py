@@ -5,7 +5,7 @@ without a CUDA device, a RuntimeError is raised.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
@@ -58,6 +58,13 @@ class TowerProblem(ctypes.Structure):
     ]
 
 
+class AdamTensor(ctypes.Structure):
+    """struct tt_adam_tensor."""
+
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("numel", c_int64)]
+
+
 # name -> (restype, argtypes); mirrors include/tt_b200.h one to one
 SIGNATURES = {
     "tt_abi_version": (I32, []),
@@ -86,6 +93,7 @@ SIGNATURES = {
     "tt_inbatch_ce_loss_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, I64, P, I64, P, P, P, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd_scaled": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I64, P, I64, P, I64, P, I64, P, P,
                                        P, I64, P]),
+    "tt_adam_step": (I32, [P, I32, c_double, c_double, c_double, F32, F32, P, P, P]),
     "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),

@@ -273,6 +273,14 @@ int tt_inbatch_ce_bwd_scaled(const void* U, int64_t ldu, const void* V, int64_t 
                         dU_colsum, dV_colsum, ws, (size_t)ws_bytes, S(stream), g_scale, g_scale2);
 }
 
+int tt_adam_step(const tt_adam_tensor* ts, int32_t count, double lr, double beta1, double beta2, float eps, float weight_decay,
+                 int64_t* step_dev, uint32_t* ticket_dev, void* stream) {
+  TT_CHECK(ts != nullptr && count >= 1 && count <= 32, "tt_adam_step: 1..32 tensors");
+  AdamTensor a[32];
+  for (int i = 0; i < count; ++i) a[i] = AdamTensor{ts[i].param, ts[i].grad, ts[i].exp_avg, ts[i].exp_avg_sq, ts[i].numel, 0};
+  return adam_step(a, count, lr, beta1, beta2, eps, weight_decay, (long long*)step_dev, ticket_dev, S(stream));
+}
+
 int tt_weighted_loss(const float* ce, const float* labels, int64_t ldl, const float* weights, int64_t B, int64_t T,
                      float* loss, float* g, void* stream) {
   return weighted_loss(ce, labels, ldl, weights, B, T, loss, g, S(stream));

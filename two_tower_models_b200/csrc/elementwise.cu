@@ -422,4 +422,99 @@ int gather_rows_bf16_batched(const GatherProblem* probs, int n, int* oob_flag, c
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused multi-tensor Adam (the reference trains with torch.optim.Adam on dense gradients, train/train.py:179,123-125):
+// one launch updates every parameter tensor of the model, HBM-bound at 28 bytes per element (read p, g, m, v; write
+// p, m, v).  Arithmetic follows torch.optim.Adam (amsgrad off): m += (g - m)(1 - b1); v = b2 v + (1 - b2) g^2;
+// p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps), optional L2 weight decay folded into g.
+// The step counter lives on the device (CUDA-graph replay): every block reads it, the last block to finish bumps it.
+// ---------------------------------------------------------------------------------------------
+static constexpr int ADAM_MAXT = 32;
+static constexpr int ADAM_CHUNK = 4096;  // elements per block
+struct AdamBatch {
+  AdamTensor t[ADAM_MAXT];
+  int block_start[ADAM_MAXT + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+adam_kernel(const __grid_constant__ AdamBatch b, double lr, double beta1d, double beta2d, float eps, float weight_decay,
+            long long* step, unsigned int* ticket) {
+  __shared__ float consts[2];
+  int p = 0;
+  while ((int)blockIdx.x >= b.block_start[p + 1]) ++p;
+  const AdamTensor& a = b.t[p];
+  if (threadIdx.x == 0) {
+    // bias corrections in double, as torch computes them on the host: 1 - beta^t cancels badly in fp32 for small t
+    const double t = (double)(*step + 1);
+    consts[0] = (float)(lr / (1.0 - pow(beta1d, t)));
+    consts[1] = (float)sqrt(1.0 - pow(beta2d, t));
+  }
+  __syncthreads();
+  const float step_size = consts[0], bc2_sqrt = consts[1];
+  const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
+  const long long base = (long long)(blockIdx.x - b.block_start[p]) * ADAM_CHUNK;
+  auto update = [&](float& pv, float gv, float& mv, float& vv) {
+    if (weight_decay != 0.f) gv = fmaf(weight_decay, pv, gv);
+    mv = fmaf(gv - mv, omb1, mv);
+    vv = fmaf(vv, beta2, omb2 * gv * gv);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv = pv - step_size * (mv / denom);
+  };
+  if (a.vec4) {
+#pragma unroll
+    for (int i = 0; i < ADAM_CHUNK / (256 * 4); ++i) {
+      const long long e = base + ((long long)i * 256 + threadIdx.x) * 4;
+      if (e + 3 < a.n) {
+        float4 pv = *reinterpret_cast<float4*>(a.p + e);
+        const float4 gv = *reinterpret_cast<const float4*>(a.g + e);
+        float4 mv = *reinterpret_cast<float4*>(a.m + e), vv = *reinterpret_cast<float4*>(a.v + e);
+        update(pv.x, gv.x, mv.x, vv.x); update(pv.y, gv.y, mv.y, vv.y);
+        update(pv.z, gv.z, mv.z, vv.z); update(pv.w, gv.w, mv.w, vv.w);
+        *reinterpret_cast<float4*>(a.p + e) = pv;
+        *reinterpret_cast<float4*>(a.m + e) = mv;
+        *reinterpret_cast<float4*>(a.v + e) = vv;
+      } else {
+        for (long long k = e; k < a.n && k < e + 4; ++k) update(a.p[k], a.g[k], a.m[k], a.v[k]);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < ADAM_CHUNK; i += 256) {
+      const long long k = base + i;
+      if (k < a.n) update(a.p[k], a.g[k], a.m[k], a.v[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {  // every block has read *step by now
+      *step += 1;
+      *ticket = 0;
+    }
+  }
+}
+int adam_step(const AdamTensor* tensors, int n, double lr, double beta1, double beta2, float eps, float weight_decay,
+              long long* step, unsigned int* ticket, cudaStream_t stream) {
+  TT_CHECK(n >= 1 && step != nullptr && ticket != nullptr, "adam_step: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += ADAM_MAXT) {
+    TT_CHECK(i0 == 0, "adam_step: at most %d tensors per call (the step counter advances once per launch)", ADAM_MAXT);
+    AdamBatch b;
+    b.n = n - i0 < ADAM_MAXT ? n - i0 : ADAM_MAXT;
+    b.block_start[0] = 0;
+    for (int i = 0; i < b.n; ++i) {
+      AdamTensor a = tensors[i0 + i];
+      TT_CHECK(a.n >= 0 && (a.n == 0 || (a.p && a.g && a.m && a.v)), "adam_step: null tensor %d", i0 + i);
+      a.vec4 = (((uintptr_t)a.p | (uintptr_t)a.g | (uintptr_t)a.m | (uintptr_t)a.v) % 16) == 0;
+      b.t[i] = a;
+      b.block_start[i + 1] = b.block_start[i] + (int)((a.n + ADAM_CHUNK - 1) / ADAM_CHUNK);
+    }
+    for (int i = b.n; i < ADAM_MAXT; ++i) b.block_start[i + 1] = b.block_start[b.n];
+    if (b.block_start[b.n] == 0) return 0;
+    KernelSpan span("adam_kernel", stream);
+    adam_kernel<<<b.block_start[b.n], 256, 0, stream>>>(b, (double)lr, (double)beta1, (double)beta2, eps, weight_decay, step, ticket);
+    TT_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return 0;
+}
+
 }  // namespace tt

@@ -144,6 +144,18 @@ struct TowerProblem {
 bool tower_fwd_supported(long long F, long long D, long long DI, long long hidden);
 int tower_fwd(const TowerProblem* problems, int n, int* oob_flag, cudaStream_t stream);
 
+// Fused multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off); *step is a device counter bumped by the launch.
+struct AdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  int vec4;  // filled by adam_step
+};
+int adam_step(const AdamTensor* tensors, int n, double lr, double beta1, double beta2, float eps, float weight_decay,
+              long long* step, unsigned int* ticket, cudaStream_t stream);
+
 int weighted_loss(const float* ce, const float* labels, long long ldl, const float* uvw, long long B, long long T,
                   float* loss, float* g, cudaStream_t stream);
 

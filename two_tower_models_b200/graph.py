@@ -10,7 +10,8 @@ captured once and replayed with a single launch.
     # gradients are in p.grad of every parameter (static tensors, overwritten by the next replay)
 
 Shapes, dtypes and the parameter set are frozen at capture time; the bf16 operand copies of the weights are
-re-packed inside the graph, so optimizer updates of the fp32 master weights between replays are honoured.
+re-packed inside the graph, so optimizer updates of the fp32 master weights between replays are honoured.  Pass
+`optimizer=FusedAdam(...)` to capture the parameter update in the same graph (warm-up steps update the weights too).
 """
 from typing import Dict, Sequence
 
@@ -20,9 +21,11 @@ ORDER = ("user_id", "user_features", "user_history", "item_id", "item_features",
 
 
 class GraphedTrainStep:
-    def __init__(self, model, example_batch: Dict[str, torch.Tensor], warmup: int = 3, post_backward=None):
+    def __init__(self, model, example_batch: Dict[str, torch.Tensor], warmup: int = 3, post_backward=None,
+                 optimizer=None):
         self.model = model
         self.post_backward = post_backward  # e.g. DataParallelContext.sync_gradients
+        self.optimizer = optimizer  # e.g. FusedAdam: its step is captured after the backward (device-side step counter)
         self.static = {k: example_batch[k].clone() for k in ORDER}
         dev = self.static["user_id"].device
         if dev.type != "cuda":
@@ -55,6 +58,8 @@ class GraphedTrainStep:
         loss.backward()
         if self.post_backward is not None:
             self.post_backward(m)
+        if self.optimizer is not None:
+            self.optimizer.step()
         return loss.detach()
 
     def load(self, batch: Dict[str, torch.Tensor], non_blocking: bool = True) -> None:
