@@ -43,7 +43,7 @@ struct CeFwdArgs {
 };
 
 // epilogue column groups of the forward kernel: FWD_EG x 4 warps, each thread owns 128 / FWD_EG columns of a row
-static constexpr int FWD_EG = 2;
+static constexpr int FWD_EG = 4;
 static constexpr int FWD_THREADS = 128 + FWD_EG * 128;
 
 template <int DP>
@@ -277,6 +277,17 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
         m = m_new;
       };
       const int n = j1 - j0;
+      if (FWD_EG >= 4) {
+        // 4 warps per scheduler: the other warps cover the TMEM load latency, one register set per thread suffices
+        float xs[CW];
+        for (int i = 0; i < n; ++i) {
+          load_tile(t + i, xs);
+          tmem_wait_ld();
+          release(t + i);
+          process(xs, j0 + i);
+          CE_FWD_STAMP(t + i, 1);
+        }
+      } else {
       float xa[CW], xb[CW];
       load_tile(t, xa);
       for (int i = 0; i < n; i += 2) {
@@ -292,6 +303,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
           process(xb, j0 + i + 1);
           CE_FWD_STAMP(t + i + 1, 1);
         }
+      }
       }
       t += n;
       if (valid) {
