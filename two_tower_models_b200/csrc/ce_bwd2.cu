@@ -25,6 +25,12 @@ template <int DP>
 struct Cfg2 {
   static constexpr int BN = DP == 256 ? 64 : 128;
   static constexpr int NS = 2;                   // score-tile buffers
+  // epilogue column groups (4 warps each).  4 groups (32 columns per thread) were measured SLOWER here (113 vs 97 us
+  // at B = N = 8192, d = 128): unlike the forward, every group also waits for its slice of E to be consumed, stores
+  // it and signals the UMMA warp, and that per-warp handshake does not shrink with the column count.
+  static constexpr int EG = 2;
+  static constexpr int THREADS = 128 + EG * 128;
+  static constexpr int XG = (DP / 32 < EG) ? DP / 32 : EG;  // groups that copy X / drain the accumulator (>= 32 columns each)
   static constexpr bool XT = DP <= 128;          // X tile resident in TMEM
   static constexpr int KBOX = DP / 64;
   static constexpr int X_BYTES = 128 * DP * 2;
@@ -41,10 +47,10 @@ struct Cfg2 {
 };
 
 template <int DP, bool COLSTATS>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(Cfg2<DP>::THREADS, 1)
 ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ TmapSet tmy, const CeBwdArgs a) {
   using Cfg = Cfg2<DP>;
-  constexpr int BN = Cfg::BN, NS = Cfg::NS;
+  constexpr int BN = Cfg::BN, NS = Cfg::NS, EG = Cfg::EG, XG = Cfg::XG;
   constexpr bool XT = Cfg::XT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -57,9 +63,9 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   uint64_t* xt_full = bars + 2;   // X tile copied into TMEM (8 epilogue warps)
   uint64_t* acc_full = bars + 3;
   uint64_t* acc_empty = bars + 4;
-  uint64_t* e_full = bars + 5;    // [2] per column half of E
-  uint64_t* e_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [NS]
+  uint64_t* e_full = bars + 5;    // [EG] per column group of E
+  uint64_t* e_empty = bars + 9;   // [EG]
+  uint64_t* s_full = bars + 13;   // [NS]
   uint64_t* s_empty = s_full + NS;
   uint64_t* y_full = s_empty + NS;
   uint64_t* y_empty = y_full + Cfg::STAGES;
@@ -86,16 +92,16 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
-    mbar_init(xt_full, 8);
+    mbar_init(xt_full, 4 * EG);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(acc_empty, 4 * EG);
+    for (int i = 0; i < EG; ++i) {
       mbar_init(&e_full[i], 4);
       mbar_init(&e_empty[i], 1);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
+      mbar_init(&s_empty[i], 4 * EG);
     }
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&y_full[i], 1);
@@ -169,14 +175,14 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       ++t1;
     };
     auto mma2 = [&](bool first) {
-      constexpr int KH = BN / 32;  // K = 16 steps per column half of E
+      constexpr int KH = BN / (16 * EG);  // K = 16 steps per column group of E
       const uint64_t dyt = desc_advance(dyt0, stage2 * Cfg::Y_BYTES);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < EG; ++h) {
         if (h == 0 && leader) CE_STAMP(1, t2, 0);
         mbar_wait(&e_full[h], t2 & 1);
         tc_fence_after();
-        if (h == 1 && leader) CE_STAMP(1, t2, 1);
+        if (h == EG - 1 && leader) CE_STAMP(1, t2, 1);
 #pragma unroll
         for (int kk = 0; kk < KH; ++kk) {
           const int k = h * KH + kk;
@@ -213,7 +219,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     const int e = (warp - 4) >> 2;
     const int q = warp & 3;
     const int wg_tid = threadIdx.x - 128 - e * 128;
-    constexpr int CH = BN / 64;  // 32-column chunks per group and tile
+    constexpr int CH = BN / (32 * EG);  // 32-column chunks per group and tile
     SegIter it(a.T, a.total, a.CT);
     int r, j0, j1;
     uint32_t t = 0, xs = 0;
@@ -224,20 +230,24 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       const long long row = (long long)r * 128 + prow;
       const bool valid = row < a.XR;
       if (XT) {
-        // copy this thread's half row of the X tile from (swizzled) shared memory into tensor memory
+        // copy this thread's part of its X row (DP / XG elements; groups >= XG have none) from (swizzled) shared
+        // memory into tensor memory
         mbar_wait(x_full, xs & 1);
-        constexpr int NCH = DP / 16;  // 16-byte chunks of one half row (DP/2 elements)
-        uint32_t xr[NCH * 4];
-        const uint8_t* atom = sx + ((e * (DP / 2)) >> 6) * 16384;
-        const uint32_t ch0 = ((e * (DP / 2)) & 63) >> 3;
+        if (e < XG) {
+          constexpr int PART = DP / XG;   // elements per thread, a multiple of 32
+          constexpr int NCH = PART / 8;   // 16-byte chunks
+          uint32_t xr[NCH * 4];
+          const uint8_t* atom = sx + ((e * PART) >> 6) * 16384;
+          const uint32_t ch0 = ((e * PART) & 63) >> 3;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const uint4 u = *reinterpret_cast<const uint4*>(atom + sw128_offset(prow, ch0 + c));
-          xr[4 * c] = u.x; xr[4 * c + 1] = u.y; xr[4 * c + 2] = u.z; xr[4 * c + 3] = u.w;
+          for (int c = 0; c < NCH; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(atom + sw128_offset(prow, ch0 + c));
+            xr[4 * c] = u.x; xr[4 * c + 1] = u.y; xr[4 * c + 2] = u.z; xr[4 * c + 3] = u.w;
+          }
+#pragma unroll
+          for (int c = 0; c < NCH / 4; ++c) tmem_st16(lane_base + Cfg::X_COL + e * (PART / 2) + c * 16, xr + 16 * c);
+          tmem_wait_st();
         }
-#pragma unroll
-        for (int c = 0; c < NCH / 4; ++c) tmem_st16(lane_base + Cfg::X_COL + e * (DP / 4) + c * 16, xr + 16 * c);
-        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(xt_full);
@@ -252,13 +262,13 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       // before tile j is transformed and are written afterwards, so their L2 round trip hides behind the tile instead
       // of stalling every tile.
       auto colstat_load = [&](int jj) -> float2 {
-        const long long col = (long long)jj * BN + e * (BN / 2) + wg_tid;
-        const bool cv = wg_tid < BN / 2 && col < a.YR;
+        const long long col = (long long)jj * BN + e * (BN / EG) + wg_tid;
+        const bool cv = wg_tid < BN / EG && col < a.YR;
         return make_float2(cv ? a.g[col] * gs : 0.f, cv ? a.lse[col] * LOG2E : 0.f);
       };
       if (COLSTATS) {
         const float2 cs0 = colstat_load(j0);
-        if (wg_tid < BN / 2) scol[e * (BN / 2) + wg_tid] = cs0;
+        if (wg_tid < BN / EG) scol[e * (BN / EG) + wg_tid] = cs0;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
       }
       for (int j = j0; j < j1; ++j, ++t) {
@@ -268,7 +278,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         if (COLSTATS && j + 1 < j1) cs_next = colstat_load(j + 1);
         mbar_wait(&s_full[buf], (t / NS) & 1);
         tc_fence_after();
-        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 0);
+        if (q == 0 && lane == 0 && e < 2) CE_STAMP(2 + e, t, 0);
         // E = g (exp(S - lse) - [positive]) for 32 columns, packed to bf16 pairs
         auto transform = [&](float* v, int c, uint32_t* out) {
           const long long n0 = (long long)j * BN + c * 32;
@@ -328,20 +338,20 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         }
         if (COLSTATS && j + 1 < j1) {
           asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");  // every thread of the group is done with tile j's
-          if (wg_tid < BN / 2) scol[e * (BN / 2) + wg_tid] = cs_next;
+          if (wg_tid < BN / EG) scol[e * (BN / EG) + wg_tid] = cs_next;
           asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
         }
-        if (q == 0 && lane == 0) CE_STAMP(2 + e, t, 1);
+        if (q == 0 && lane == 0 && e < 2) CE_STAMP(2 + e, t, 1);
       }
       // segment accumulator -> partial slot (each group drains half of the columns)
       mbar_wait(acc_full, xs & 1);
       tc_fence_after();
-      {
+      if (e < XG) {
         const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
         float* dst = a.partial + (long long)slot * a.slot_stride + row * DP;
 #pragma unroll 1
-        for (int c = 0; c < DP / 64; ++c) {
-          const int col = e * (DP / 2) + c * 32;
+        for (int c = 0; c < DP / (32 * XG); ++c) {
+          const int col = e * (DP / XG) + c * 32;
           float v[32];
           tmem_ld32(lane_base + Cfg::ACC_COL + col, v);
           tmem_wait_ld();
@@ -378,7 +388,7 @@ int launch2(const TmapSet& tx, const TmapSet& ty, const CeBwdArgs& a, int grid, 
     configured = true;
   }
   KernelSpan span(COLSTATS ? "ce_bwd2_kernel_dV" : "ce_bwd2_kernel_dU", st);
-  ce_bwd2_kernel<DP, COLSTATS><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
+  ce_bwd2_kernel<DP, COLSTATS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tx, ty, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
