@@ -37,9 +37,11 @@ def towers_fwd():
     m._packed.invalidate()
     with torch.no_grad():
         fu, fi = m.user_features_arch, m.item_features_arch
-        return ops.TowerSetFunction.apply([("user", None), ("item", None)], m._packed,
+        out = ops.TowerSetFunction.apply([("user", None), ("item", None)], m._packed,
             b["user_id"], b["user_features"], None, m.user_id_embedding_arch.weight, fu[0].weight, fu[0].bias, fu[2].weight, fu[2].bias, m.user_tower_arch.weight, m.user_tower_arch.bias,
             b["item_id"], b["item_features"], None, m.item_id_embedding_arch.weight, fi[0].weight, fi[0].bias, fi[2].weight, fi[2].bias, m.item_tower_arch.weight, m.item_tower_arch.bias)
+        ops.join_pending_fills()  # train_forward does this after the loss forward
+        return out
 
 def fwd_only():
     m._packed.invalidate()

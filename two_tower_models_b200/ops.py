@@ -892,6 +892,17 @@ def _aux_stream(device, idx: int = 0) -> "torch.cuda.Stream":
 
 
 _PARALLEL_BACKWARD = os.environ.get("TT_B200_PARALLEL_BACKWARD", "1") == "1"
+_LATE_ZERO_FILL = os.environ.get("TT_B200_LATE_ZERO_FILL", "1") == "1"
+_pending_fills = []  # (device, event) of side-stream zero fills that the current stream has not joined yet
+
+
+def join_pending_fills() -> None:
+    """Make the current stream wait for the dense table-gradient zero fills that TowerSetFunction.forward started on
+    the side stream.  train_forward calls this after the loss forward (the fills then ran beside the scoring kernels,
+    and a CUDA-graph capture of a forward-only call still ends with every stream joined)."""
+    while _pending_fills:
+        device, ev = _pending_fills.pop()
+        torch.cuda.current_stream(device).wait_event(ev)
 
 
 def _stage_weight(packed: PackedWeights, key, param, casts, segments=None) -> torch.Tensor:
@@ -966,17 +977,23 @@ class TowerSetFunction(torch.autograd.Function):
                 d["b0"], d["b1"], d["bt"] = _f32c(b0), _f32c(b1), _f32c(bt)
                 tw.append(d)
             # dense embedding-table gradients (the reference's nn.Embedding(sparse=False) semantics) need a zero
-            # fill of hash x D floats per step: start it now on a side stream, it overlaps the forward kernels
+            # fill of hash x D floats per step (2 x 51 MB at the benchmark config).  It runs on a side stream: forked
+            # AFTER the tower kernel by default, so that it shares the device with the loss kernels (which move 4 MB)
+            # instead of competing with the tower kernel's gathers for HBM, and joined when the backward needs it.
             zero_jobs = [d for t, d in enumerate(tw) if ctx.needs_input_grad[2 + 10 * t + 3]]
-            if zero_jobs:
-                cur = torch.cuda.current_stream(zero_jobs[0]["feats16"].device)
+            def start_fills():
+                cur_ = torch.cuda.current_stream(zero_jobs[0]["feats16"].device)
                 aux = _aux_stream(zero_jobs[0]["feats16"].device)
-                aux.wait_stream(cur)
+                aux.wait_stream(cur_)
                 with torch.cuda.stream(aux):
                     for d in zero_jobs:
-                        d["dtable"] = torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=cur.device)
-                    ev = torch.cuda.Event()
-                    ev.record(aux)
+                        d["dtable"] = torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=cur_.device)
+                    ev_ = torch.cuda.Event()
+                    ev_.record(aux)
+                return cur_, ev_
+
+            if zero_jobs and not _LATE_ZERO_FILL:
+                cur, ev = start_fills()
             if casts:
                 cast_batched(casts)
             fused = [d for d in tw if d["fused"]]
@@ -997,8 +1014,13 @@ class TowerSetFunction(torch.autograd.Function):
                                    out16=d["X16"][:, d["D8"]:]) for d in layered])
                 gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
                                    out16=d["emb16"]) for d in layered])
-            if zero_jobs:  # join the side stream again (the fills are long done: they ran beside the kernels above)
+            if zero_jobs and not _LATE_ZERO_FILL:  # join again (the fills ran beside the kernels above)
                 cur.wait_event(ev)
+                for d in zero_jobs:
+                    d["dtable"].record_stream(cur)
+            elif zero_jobs:  # fork now; the caller joins after the loss forward (join_pending_fills), else backward does
+                cur, ev = start_fills()
+                _pending_fills.append((cur.device, ev))
                 for d in zero_jobs:
                     d["dtable"].record_stream(cur)
         ctx.tw = tw
@@ -1013,6 +1035,7 @@ class TowerSetFunction(torch.autograd.Function):
         tw = ctx.tw
         T = len(tw)
         dev = dembs[0].device
+        join_pending_fills()  # no-op when train_forward already joined the table-gradient fills
         casts = []
         for d, demb in zip(tw, dembs):
             if demb is None:  # this tower's embedding did not reach the loss

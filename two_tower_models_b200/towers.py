@@ -221,9 +221,11 @@ class TwoTowerBaseRetrieval(nn.Module):
         else:
             user_embedding = self.compute_user_embedding(user_id, user_features, user_history)
             item_embeddings = self.compute_item_embeddings(item_id, item_features)
-        return self.compute_training_loss(
+        loss = self.compute_training_loss(
             user_embedding=user_embedding, item_embeddings=item_embeddings, position=position, labels=labels
         )
+        ops.join_pending_fills()  # dense table-gradient zero fills ran beside the scoring kernels
+        return loss
 
 
 class TwoTowerWithUserHistoryEncoder(TwoTowerBaseRetrieval):
