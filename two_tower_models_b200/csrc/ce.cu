@@ -1,23 +1,24 @@
-// Fused in-batch sampled-softmax cross entropy for sm_100a (forward and backward).
+// Fused in-batch sampled-softmax cross entropy for sm_100a: forward kernel, merge kernels, host side of the backward.
 //
 // Reference semantics: src/two_tower_base_retrieval.py:287 (S = U V^T), :301 (target = arange),
-// :310-312 (F.cross_entropy(reduction="none")) and autograd of the same (train/train.py:124).
-// The [B,N] score matrix never exists in HBM: 128xBN score tiles are produced by tcgen05.mma into
-// TMEM from TMA-staged bf16 operand tiles and consumed in place.
+// :310-312 (F.cross_entropy(reduction="none")), :322-343 (label weights, batch max, weighted mean) and autograd
+// of the same (train/train.py:124).  The [B,N] score matrix never exists in HBM: 128x128 score tiles are
+// produced by tcgen05.mma into TMEM from TMA-staged bf16 operand tiles and consumed in place.
 //
-//   forward : per 128-row tile, running (max, sum-exp) over column tiles + the target logit.
-//   backward: one generic "flash" kernel  acc[128, d] = sum_j E_j * Y_j,  E_j = f(X Y_j^T), run twice:
+//   forward : per 128-row tile, running (max, sum-exp) over the column tiles (ce_fwd_kernel); a merge kernel folds
+//             the per-(slot, column group) partials, recomputes the positive's logit from the operands and - with the
+//             identity debias hook - also forms the label weights, their batch maximum and the weighted mean.
+//   backward: ce_bwd2.cu runs  acc[128, d] = sum_j E_j * Y_j,  E_j = f(X Y_j^T)  twice:
 //       pass A  X=U, Y=V, E_ij = g_i (exp(S_ij - lse_i) - [j == i+off])           -> dU
 //       pass B  X=V, Y=U, E_ji = g_i (exp(S_ij - lse_i) - [j == i+off]) (col stats) -> dV
-//     E is written as bf16 into a 128B-swizzled smem tile and fed back as the A operand of the second
-//     UMMA, whose B operand is the same Y tile read MN-major.
+//     and ce_bwd_reduce_kernel (here) merges the slot partials of both passes in one launch.
 //
 // Work is the flattened (row tile, column tile) space cut into equal contiguous ranges, one per SM
 // (persistent CTAs).  A CTA's range touches <= a few row tiles ("segments"); every segment writes a
 // partial result into a slot and a small second kernel merges the slots.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
-// warps 4-7 / 8-11 two epilogue warpgroups that alternate score tiles (TMEM buffer e <-> group e).
+// Warp roles of ce_fwd_kernel (640 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
+// warps 4-19 epilogue: 4 column groups x 4 TMEM lane quarters, every thread owns 32 columns of one row of each tile.
 #include <stdlib.h>
 
 #include "ce_common.cuh"

@@ -1,6 +1,6 @@
 // In-batch cross-entropy backward, v2: the E = g (softmax - onehot) tile and the X tile live in TENSOR MEMORY.
 //
-// Same math and scheduling as ce_bwd_kernel (ce.cu):  acc[128, d] = sum_j E_j Y_j,  E_j = f(X Y_j^T), run
+// Math and scheduling (see ce.cu):  acc[128, d] = sum_j E_j Y_j,  E_j = f(X Y_j^T), run
 // once for dU (X=U, Y=V, row statistics) and once for dV (X=V, Y=U, column statistics).  What changed is
 // where the UMMA A operands come from.  With both operands in shared memory a 128x128x16 UMMA reads 8 KB per
 // 64 tensor-pipe cycles = the full 128 B/clk of shared-memory bandwidth, and the measured issue interval was
