@@ -72,3 +72,50 @@ def test_host_mirrors_keep_reference_names():
     for name in ("get_user_embedding", "process_user_features", "compute_user_embedding", "compute_item_embeddings",
                  "forward", "debias_net_user_value", "compute_training_loss", "train_forward"):
         assert callable(getattr(b, name))
+
+
+@pytest.mark.parametrize("kind,cls_name", [("position", "TwoTowerWithPositionDebiasedWeights"),
+                                           ("user", "TwoTowerWithUserDebiasedWeights"),
+                                           ("both", "TwoTowerWithDebiasing")])
+def test_debias_mirrors_keep_reference_names_and_hook_math(kind, cls_name):
+    """The debias drop-ins carry the reference subclasses' parameter names (state_dict of the golden, produced by the
+    unmodified reference, loads strictly) and their hook bodies - plain tensor code - reproduce the oracle's
+    restatement of the reference hooks on CPU tensors."""
+    import oracle
+    import two_tower_models_b200 as tt
+
+    g = load_golden(f"debias_{kind}.npz")
+    p, batch = section(g, "p:"), section(g, "in:")
+    DU, DI = p["user_id_embedding_arch.weight"].shape[1], p["item_id_embedding_arch.weight"].shape[1]
+    m = getattr(tt, cls_name)(
+        5, p["user_id_embedding_arch.weight"].shape[0], DU, p["user_features_arch.0.weight"].shape[1],
+        batch["user_history"].shape[1], p["item_id_embedding_arch.weight"].shape[0], DI,
+        p["item_features_arch.0.weight"].shape[1], g["attr:user_value_weights"].tolist(), tt.BaselineMIPSModule(16, DI),
+    )
+    assert set(m.state_dict().keys()) == set(p.keys())
+    m.load_state_dict(p, strict=True)
+    nuv = oracle.net_user_value(batch["labels"], g["attr:user_value_weights"])
+    u = g["out:user_embedding"]
+    got_w, got_loss = m.debias_net_user_value(net_user_value=nuv, position=batch["position"], user_embedding=u)
+    ref_w, ref_loss = oracle.DEBIAS_HOOKS[kind](p, nuv, batch["position"], u)
+    assert torch.allclose(got_w, ref_w, rtol=1e-6, atol=1e-7) and torch.allclose(got_loss, ref_loss, rtol=1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_fused_adam_and_graph_step_refuse_cpu_tensors():
+    import two_tower_models_b200 as tt
+    from two_tower_models_b200.graph import GraphedTrainStep
+
+    w = torch.nn.Parameter(torch.randn(8, 4))
+    w.grad = torch.randn(8, 4)
+    opt = tt.FusedAdam([w], lr=1e-3)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(ValueError):
+        tt.FusedAdam([w], lr=-1.0)
+    m = tt.TwoTowerBaseRetrieval(4, 20, 16, 8, 20, 16, 8, [1.0], tt.BaselineMIPSModule(16, 16))
+    batch = dict(user_id=torch.zeros(4, dtype=torch.int64), user_features=torch.randn(4, 8),
+                 user_history=torch.zeros(4, 2, dtype=torch.int64), item_id=torch.zeros(4, dtype=torch.int64),
+                 item_features=torch.randn(4, 8), position=torch.zeros(4, dtype=torch.int64), labels=torch.ones(4, 1))
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(m, batch)
