@@ -37,8 +37,9 @@ RING = 32  # distinct input batches cycled through: 32 x ~8.5 MB = 272 MB > 126 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    # defaults: ~0.3 s of timed device work per leg, long enough for the 50 ms nvidia-smi clock sampler to see the load
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--d", type=int, default=128)
     ap.add_argument("--batch", type=int, default=8192, help="rows per GPU")
