@@ -21,6 +21,8 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
+if os.environ.get("TT_CE_BWD_LEAN") == "1":  # candidate epilogue of the CE backward (ce_bwd2.cu), not yet measured
+    FLAGS.append("-DTT_CE_BWD_LEAN")
 if os.environ.get("TT_CE_BRINGUP") == "1":  # clock64 timelines / partial epilogues of the CE kernels (tools/trace_ce.py)
     FLAGS.append("-DTT_CE_BRINGUP")
 

@@ -72,6 +72,14 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// TT_CE_BWD_LEAN (candidate for the next round, default off until measured on a B200): the epilogue's bookkeeping
+// is cut the way the forward's was - bring-up stamps compiled out, 32-bit column arithmetic, the positive handled on
+// the one tile that holds it - ncu counted ~150 bookkeeping instructions around 224 of math per warp and tile.
+#if defined(TT_CE_BWD_LEAN) && !defined(TT_CE_BRINGUP)
+#define CTA_TIME(slot) do { } while (0)
+#define CE_STAMP(role, tile, which) do { } while (0)
+#else
+#define TT_CE_BWD_HOOKS 1
 #define CTA_TIME(slot)                                                          \
   do {                                                                          \
     if (a.cta_times != nullptr && threadIdx.x == 96) {                          \
@@ -85,6 +93,7 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   do {                                                                                        \
     if (a.trace != nullptr && blockIdx.x == 0 && (tile) < 64) a.trace[((role) * 64 + (tile)) * 2 + (which)] = clock64(); \
   } while (0)
+#endif
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < tmx.n; ++p) tma_prefetch_desc(&tmx.m[p]);
     for (int p = 0; p < tmy.n; ++p) tma_prefetch_desc(&tmy.m[p]);
@@ -258,6 +267,11 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         rl = valid ? a.lse[row] * LOG2E : 0.f;
       }
       const long long tgt = row + a.diag_shift;
+#ifdef TT_CE_BWD_LEAN
+      // tile / 32-column chunk / column of this row's positive (-1: none among the YR columns)
+      const int tgt_i = (valid && tgt >= 0 && tgt < a.YR) ? (int)tgt : -1;
+      const int jd = tgt_i >= 0 ? tgt_i / BN : -1, cd = tgt_i >= 0 ? (tgt_i % BN) >> 5 : -1, od = tgt_i & 31;
+#endif
       // column statistics (g, lse) of the tile's columns live in shared memory: the loads for tile j + 1 are issued
       // before tile j is transformed and are written afterwards, so their L2 round trip hides behind the tile instead
       // of stalling every tile.
@@ -281,15 +295,19 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         if (q == 0 && lane == 0 && e < 2) CE_STAMP(2 + e, t, 0);
         // E = g (exp(S - lse) - [positive]) for 32 columns, packed to bf16 pairs
         auto transform = [&](float* v, int c, uint32_t* out) {
+#ifndef TT_CE_BWD_LEAN
           const long long n0 = (long long)j * BN + c * 32;
+#endif
           if (!COLSTATS) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
+#ifndef TT_CE_BWD_LEAN
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (n0 + i == tgt) v[i] -= rs;
             }
+#endif
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {  // (g, lse) of two columns per 16-byte broadcast load
@@ -297,12 +315,21 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
               v[i] = cc4.x * ex2f(fmaf(v[i], LOG2E, -cc4.y));
               v[i + 1] = cc4.z * ex2f(fmaf(v[i + 1], LOG2E, -cc4.w));
             }
+#ifndef TT_CE_BWD_LEAN
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (n0 + i == tgt) v[i] -= sc[c * 32 + i].x;
             }
+#endif
           }
+#ifdef TT_CE_BWD_LEAN
+          if (j == jd && c == cd) {  // the one chunk of the one tile that holds this row's positive
+            const float sub = COLSTATS ? sc[c * 32 + od].x : rs;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] -= (i == od) ? sub : 0.f;
+          }
+#endif
 #pragma unroll
           for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         };
