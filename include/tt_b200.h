@@ -159,6 +159,33 @@ typedef struct tt_tower_problem {
 int32_t tt_tower_fwd_supported(int64_t F, int64_t D, int64_t DI, int64_t hidden);
 int tt_tower_fwd(const tt_tower_problem* problems, int32_t count, int32_t* oob_flag, void* stream);
 
+/* CANDIDATE (not on the default path yet): the activation-gradient chain of the tower backward in one
+ * launch for `count` (<= 4) towers of a shape tt_tower_fwd_supported() accepts (F = D): dx_bf16 = demb Wt (both halves),
+ * table_grad[ids[r], :] += dX[r, 0:D] in fp32 (skipped when table_grad is NULL), dh_bf16 = (dX[:, D:2D] W1) where h > 0,
+ * dxsum[D + c] += sum_r dX[r, D + c] (bias gradient of MLP layer 1), db0[c] += sum_r dH[r, c].  The weight gradients
+ * stay tt_gemm_bf16 (split-K) launches. */
+typedef struct tt_tower_bwd_problem {
+  const void* demb_bf16;
+  int64_t ld_demb;
+  const int64_t* ids;
+  int64_t table_rows;
+  const void* wt_bf16;
+  int64_t ldwt;
+  const void* w1_bf16;
+  int64_t ldw1;
+  const void* h_bf16;
+  int64_t ldh;
+  void* dx_bf16;
+  int64_t lddx;
+  void* dh_bf16;
+  int64_t lddh;
+  float* table_grad;
+  float* dxsum;
+  float* db0;
+  int64_t rows, D, DI, hidden;
+} tt_tower_bwd_problem;
+int tt_tower_bwd_chain(const tt_tower_bwd_problem* problems, int32_t count, void* stream);
+
 /* ---- in-batch sampled-softmax loss ---------------------------------------------------------- */
 
 /* Scratch bytes needed by tt_inbatch_ce_fwd / _bwd for this shape on the current device. */

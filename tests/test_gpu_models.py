@@ -144,6 +144,30 @@ def test_fused_tower_kernel_matches_layered_path(B, d, monkeypatch):
             assert rel_fro(outs["1"][0], outs["0"][0]) < 1e-5
 
 
+@pytest.mark.skipif(__import__("os").environ.get("TT_B200_FUSED_TOWER_BWD") != "1",
+                    reason="candidate kernel (csrc/tower_bwd.cu), opt-in: TT_B200_FUSED_TOWER_BWD=1")
+@pytest.mark.parametrize("B,d", [(300, 128), (1024, 128), (200, 64)])
+def test_fused_tower_backward_chain_matches_layered_path(B, d, monkeypatch):
+    """tt_tower_bwd_chain (dX, dH, table scatter, db1 / db0 in one launch) against the per-GEMM backward on the same
+    step: every parameter gradient agrees to bf16 rounding of dX (the fused path scatters fp32 rows into the table
+    gradient, the layered path the bf16 copy)."""
+    from two_tower_models_b200 import ops
+
+    F, T = d, 1
+    p = _random_base_params(d, d, F, F, 500, 500, seed=B)
+    uvw = torch.tensor([1.0])
+    batch = _random_batch(B, F, F, 500, 500, T, seed=B + 1)
+    grads = {}
+    for flag in (False, True):
+        monkeypatch.setattr(ops, "_FUSED_TOWER_BWD", flag)
+        m = _build_base(p, uvw)
+        _run(m, batch)
+        grads[flag] = {k: prm.grad.detach().clone() for k, prm in m.named_parameters()}
+    for k in grads[False]:
+        assert_close_fro(grads[True][k], grads[False][k], rtol=1e-2, atol=BIAS_ATOL if grads[False][k].dim() == 1 else GRAD_ATOL,
+                         what=k)
+
+
 def test_base_model_edge_cases():
     """All-zero labels => plain mean CE; labels given as [B] (train/train.py quirk); hook override is honoured."""
     import two_tower_models_b200 as tt

@@ -58,6 +58,18 @@ class TowerProblem(ctypes.Structure):
     ]
 
 
+class TowerBwdProblem(ctypes.Structure):
+    """struct tt_tower_bwd_problem."""
+
+    _fields_ = [
+        ("demb_bf16", c_void_p), ("ld_demb", c_int64), ("ids", c_void_p), ("table_rows", c_int64),
+        ("wt_bf16", c_void_p), ("ldwt", c_int64), ("w1_bf16", c_void_p), ("ldw1", c_int64),
+        ("h_bf16", c_void_p), ("ldh", c_int64), ("dx_bf16", c_void_p), ("lddx", c_int64),
+        ("dh_bf16", c_void_p), ("lddh", c_int64), ("table_grad", c_void_p), ("dxsum", c_void_p), ("db0", c_void_p),
+        ("rows", c_int64), ("D", c_int64), ("DI", c_int64), ("hidden", c_int64),
+    ]
+
+
 class AdamTensor(ctypes.Structure):
     """struct tt_adam_tensor."""
 
@@ -84,6 +96,7 @@ SIGNATURES = {
     "tt_gather_rows_bf16_batched": (I32, [P, I32, P, P]),
     "tt_tower_fwd_supported": (I32, [I64, I64, I64, I64]),
     "tt_tower_fwd": (I32, [P, I32, P, P]),
+    "tt_tower_bwd_chain": (I32, [P, I32, P]),
     "tt_inbatch_ce_workspace_bytes": (I64, [I64, I64, I64]),
     "tt_inbatch_ce_fwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_inbatch_ce_bwd": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P, I64, P, I64, P, I64, P, P, P, I64, P]),

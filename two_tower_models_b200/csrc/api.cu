@@ -225,6 +225,18 @@ int tt_tower_fwd(const tt_tower_problem* pr, int32_t count, int32_t* oob_flag, v
   return tower_fwd(t, count, oob_flag, S(stream));
 }
 
+int tt_tower_bwd_chain(const tt_tower_bwd_problem* pr, int32_t count, void* stream) {
+  TT_CHECK(pr != nullptr && count >= 1 && count <= 4, "tt_tower_bwd_chain: 1..4 towers");
+  TowerBwdProblem t[4];
+  for (int i = 0; i < count; ++i) {
+    const tt_tower_bwd_problem& q = pr[i];
+    t[i] = TowerBwdProblem{q.demb_bf16, q.ld_demb, (const long long*)q.ids, q.table_rows, q.wt_bf16, q.ldwt, q.w1_bf16, q.ldw1,
+                           q.h_bf16, q.ldh, q.dx_bf16, q.lddx, q.dh_bf16, q.lddh, q.table_grad, q.dxsum, q.db0, q.rows, q.D, q.DI,
+                           q.hidden};
+  }
+  return tower_bwd_chain(t, count, S(stream));
+}
+
 int64_t tt_inbatch_ce_workspace_bytes(int64_t B, int64_t N, int64_t d) {
   return (int64_t)inbatch_ce_workspace_bytes(B, N, d);
 }

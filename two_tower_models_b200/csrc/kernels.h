@@ -141,6 +141,28 @@ struct TowerProblem {
   long long ld_emb16;
   long long rows, F, D, DI, hidden;
 };
+// Fused tower backward chain (tower_bwd.cu, candidate): dX = demb Wt, dH = (dFe W1) masked, table scatter, db1 / db0.
+struct TowerBwdProblem {
+  const void* demb16;  // bf16 [rows, DI]
+  long long ld_demb;
+  const long long* ids;
+  long long table_rows;
+  const void* wt;  // bf16 [DI, 2D]
+  long long ldwt;
+  const void* w1;  // bf16 [D, hidden]
+  long long ldw1;
+  const void* h16;  // bf16 [rows, hidden]
+  long long ldh;
+  void* dx16;  // out bf16 [rows, 2D]
+  long long lddx;
+  void* dh16;  // out bf16 [rows, hidden]
+  long long lddh;
+  float* dtable;  // += [table_rows, D] or null
+  float* dxsum;   // += [2D] (feature half only)
+  float* db0;     // += [hidden]
+  long long rows, D, DI, hidden;
+};
+int tower_bwd_chain(const TowerBwdProblem* problems, int n, cudaStream_t stream);
 bool tower_fwd_supported(long long F, long long D, long long DI, long long hidden);
 int tower_fwd(const TowerProblem* problems, int n, int* oob_flag, cudaStream_t stream);
 

@@ -880,6 +880,26 @@ def tower_forward_fused(towers) -> None:
     _maybe_check_ids(towers[0]["feats"].device, "gather_rows")
 
 
+_FUSED_TOWER_BWD = os.environ.get("TT_B200_FUSED_TOWER_BWD", "0") == "1"  # candidate, see csrc/tower_bwd.cu
+
+
+def tower_backward_chain_fused(towers) -> None:
+    """dX, dH, the dense table gradients and the db1 / db0 column sums of every tower in one launch
+    (tt_tower_bwd_chain); towers: dicts with demb16, ids, wt_16, w1_16, H16, dX16, dH16, dtable_buf, dXsum, db0."""
+    arr = (_native.TowerBwdProblem * len(towers))()
+    for t, d in zip(arr, towers):
+        t.demb_bf16, t.ld_demb = d["demb16"].data_ptr(), d["demb16"].stride(0)
+        t.ids, t.table_rows = d["ids"].data_ptr(), d["table_rows"]
+        t.wt_bf16, t.ldwt = d["wt_16"].data_ptr(), d["wt_16"].stride(0)
+        t.w1_bf16, t.ldw1 = d["w1_16"].data_ptr(), d["w1_16"].stride(0)
+        t.h_bf16, t.ldh = d["H16"].data_ptr(), d["H16"].stride(0)
+        t.dx_bf16, t.lddx = d["dX16"].data_ptr(), d["dX16"].stride(0)
+        t.dh_bf16, t.lddh = d["dH16"].data_ptr(), d["dH16"].stride(0)
+        t.table_grad, t.dxsum, t.db0 = d["dtable_buf"].data_ptr(), d["dXsum"].data_ptr(), d["db0"].data_ptr()
+        t.rows, t.D, t.DI, t.hidden = d["B"], d["D"], d["DI"], d["hid"]
+    _native.check(_native.lib().tt_tower_bwd_chain(arr, len(towers), _stream()), "tower_bwd_chain")
+
+
 _aux_streams = {}
 
 
@@ -1072,36 +1092,51 @@ class TowerSetFunction(torch.autograd.Function):
         for d in tw:  # buffers are allocated on the main stream; zero-filled beside the forward kernels when possible
             pre = d.pop("dtable", None)
             d["dtable_buf"] = pre if pre is not None else torch.zeros((d["table_rows"], d["D"]), dtype=torch.float32, device=dev)
-        if par:
-            s1.wait_stream(cur)
-        with torch.cuda.stream(s1):  # dWt = demb^T X (split-K over the batch)
+        chain = (_FUSED_TOWER_BWD and all(d["fused"] and d["row_exchange"] is None for d in tw)
+                 and len({(d["D"], d["DI"]) for d in tw}) == 1 and len(tw) <= 4)
+        if chain:
+            # candidate path: dX, dH, both table scatter-adds and the two bias column sums in ONE launch, then the three
+            # weight-gradient GEMMs of every tower in one batched split-K launch
+            tower_backward_chain_fused(tw)
             gemm_batched([dict(A=d["demb16"], B=d["X16"], M=d["DI"], N=d["KT"], K=d["B"], a_mn=True, b_mn=True,
                                out32=d["dWt_p"], accumulate=True) for d in tw])
-        # dX = demb Wt (+ fp32 column sums = bias gradient of the second MLP layer)
-        gemm_batched([dict(A=d["demb16"], B=d["wt_16"], M=d["B"], N=d["KT"], K=d["DI"], b_mn=True, out16=d["dX16"],
-                           colsum=d["dXsum"]) for d in tw])
-        if par:
-            s1.wait_stream(cur)
-            s2.wait_stream(cur)
-        with torch.cuda.stream(s1):  # dW1 = dFe^T H
             gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
                                out32=d["dW1"], accumulate=True) for d in tw])
-        with torch.cuda.stream(s2):  # id embeddings (dense gradient, duplicates accumulate)
+            gemm_batched([dict(A=d["dH16"], B=d["feats16"], M=d["hid"], N=d["F"], K=d["B"], a_mn=True, b_mn=True,
+                               out32=d["dW0"], accumulate=True) for d in tw])
             for d in tw:
-                pre = d.pop("dtable_buf")
-                if d["row_exchange"] is not None:
-                    ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :d["D8"]].contiguous())
-                    d["dtable_out"] = scatter_add_rows(rows_all, ids_all, d["D"], d["table_rows"], col_offset=0, grad=pre)
-                else:
-                    d["dtable_out"] = scatter_add_rows(d["dX16"], d["ids"], d["D"], d["table_rows"], col_offset=0, grad=pre)
-        # dH = (dFe W1) masked by ReLU (+ column sums = bias gradient of layer 0)
-        gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["w1_16"], M=d["B"], N=d["hid"], K=d["D"], b_mn=True,
-                           relu_mask=d["H16"], out16=d["dH16"], colsum=d["db0"]) for d in tw])
-        gemm_batched([dict(A=d["dH16"], B=d["feats16"], M=d["hid"], N=d["F"], K=d["B"], a_mn=True, b_mn=True,
-                           out32=d["dW0"], accumulate=True) for d in tw])
-        if par:
-            cur.wait_stream(s1)
-            cur.wait_stream(s2)
+                d["dtable_out"] = d.pop("dtable_buf")
+        if not chain:
+            if par:
+                s1.wait_stream(cur)
+            with torch.cuda.stream(s1):  # dWt = demb^T X (split-K over the batch)
+                gemm_batched([dict(A=d["demb16"], B=d["X16"], M=d["DI"], N=d["KT"], K=d["B"], a_mn=True, b_mn=True,
+                                   out32=d["dWt_p"], accumulate=True) for d in tw])
+            # dX = demb Wt (+ fp32 column sums = bias gradient of the second MLP layer)
+            gemm_batched([dict(A=d["demb16"], B=d["wt_16"], M=d["B"], N=d["KT"], K=d["DI"], b_mn=True, out16=d["dX16"],
+                               colsum=d["dXsum"]) for d in tw])
+            if par:
+                s1.wait_stream(cur)
+                s2.wait_stream(cur)
+            with torch.cuda.stream(s1):  # dW1 = dFe^T H
+                gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
+                                   out32=d["dW1"], accumulate=True) for d in tw])
+            with torch.cuda.stream(s2):  # id embeddings (dense gradient, duplicates accumulate)
+                for d in tw:
+                    pre = d.pop("dtable_buf")
+                    if d["row_exchange"] is not None:
+                        ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :d["D8"]].contiguous())
+                        d["dtable_out"] = scatter_add_rows(rows_all, ids_all, d["D"], d["table_rows"], col_offset=0, grad=pre)
+                    else:
+                        d["dtable_out"] = scatter_add_rows(d["dX16"], d["ids"], d["D"], d["table_rows"], col_offset=0, grad=pre)
+            # dH = (dFe W1) masked by ReLU (+ column sums = bias gradient of layer 0)
+            gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["w1_16"], M=d["B"], N=d["hid"], K=d["D"], b_mn=True,
+                               relu_mask=d["H16"], out16=d["dH16"], colsum=d["db0"]) for d in tw])
+            gemm_batched([dict(A=d["dH16"], B=d["feats16"], M=d["hid"], N=d["F"], K=d["B"], a_mn=True, b_mn=True,
+                               out32=d["dW0"], accumulate=True) for d in tw])
+            if par:
+                cur.wait_stream(s1)
+                cur.wait_stream(s2)
         grads = []
         for d in tw:
             D, D8, E, KT = d["D"], d["D8"], d["E"], d["KT"]
