@@ -268,6 +268,11 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       }
       const long long tgt = row + a.diag_shift;
 #ifdef TT_CE_BWD_LEAN
+      // row pass: |g| folded into the exponent (g exp2(x) = sign(g) exp2(x + log2|g|); g = 0 gives exp2(-inf) = 0), the
+      // sign goes onto the packed bf16 pairs - one multiply per element less
+      const float rl2 = rl - log2f(fabsf(rs));
+      const float rs_abs = fabsf(rs);
+      const uint32_t sgn = (!COLSTATS && rs < 0.f) ? 0x80008000u : 0u;
       // tile / 32-column chunk / column of this row's positive (-1: none among the YR columns)
       const int tgt_i = (valid && tgt >= 0 && tgt < a.YR) ? (int)tgt : -1;
       const int jd = tgt_i >= 0 ? tgt_i / BN : -1, cd = tgt_i >= 0 ? (tgt_i % BN) >> 5 : -1, od = tgt_i & 31;
@@ -299,8 +304,13 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
           const long long n0 = (long long)j * BN + c * 32;
 #endif
           if (!COLSTATS) {
+#ifdef TT_CE_BWD_LEAN
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ex2f(fmaf(v[i], LOG2E, -rl2));
+#else
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = rs * ex2f(fmaf(v[i], LOG2E, -rl));
+#endif
 #ifndef TT_CE_BWD_LEAN
             if (tgt >= n0 && tgt < n0 + 32) {
 #pragma unroll
@@ -325,13 +335,18 @@ ce_bwd2_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
           }
 #ifdef TT_CE_BWD_LEAN
           if (j == jd && c == cd) {  // the one chunk of the one tile that holds this row's positive
-            const float sub = COLSTATS ? sc[c * 32 + od].x : rs;
+            const float sub = COLSTATS ? sc[c * 32 + od].x : rs_abs;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] -= (i == od) ? sub : 0.f;
           }
 #endif
+#ifdef TT_CE_BWD_LEAN
+#pragma unroll
+          for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) ^ sgn;
+#else
 #pragma unroll
           for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#endif
         };
         const uint32_t s_addr = lane_base + buf * BN + e * (CH * 32);
         const uint32_t e_addr = lane_base + Cfg::E_COL + e * (CH * 16);
