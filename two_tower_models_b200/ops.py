@@ -1012,7 +1012,9 @@ class TowerSetFunction(torch.autograd.Function):
                     ev_.record(aux)
                 return cur_, ev_
 
-            if zero_jobs and not _LATE_ZERO_FILL:
+            # data parallel keeps the fills inside this function (the path that was measured on 2 GPUs)
+            late_fill = _LATE_ZERO_FILL and all(spec[1] is None for spec in specs)
+            if zero_jobs and not late_fill:
                 cur, ev = start_fills()
             if casts:
                 cast_batched(casts)
@@ -1034,7 +1036,7 @@ class TowerSetFunction(torch.autograd.Function):
                                    out16=d["X16"][:, d["D8"]:]) for d in layered])
                 gemm_batched([dict(A=d["X16"], B=d["wt_16"], M=d["B"], N=d["DI"], K=d["KT"], bias=d["bt"], out32=d["emb"],
                                    out16=d["emb16"]) for d in layered])
-            if zero_jobs and not _LATE_ZERO_FILL:  # join again (the fills ran beside the kernels above)
+            if zero_jobs and not late_fill:  # join again (the fills ran beside the kernels above)
                 cur.wait_event(ev)
                 for d in zero_jobs:
                     d["dtable"].record_stream(cur)
