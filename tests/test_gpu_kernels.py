@@ -215,6 +215,31 @@ def test_inbatch_ce_backward(B, N, d, off):
     assert_close_fro(dV16[:, :d].float(), dV_ref, rtol=8e-3, what="dV bf16")
 
 
+@pytest.mark.parametrize("B,N,d,off", [(300, 300, 128, 0), (256, 1024, 128, 512), (512, 512, 64, 0), (200, 456, 256, 101)])
+def test_inbatch_ce_backward_signed_and_scaled_g(B, N, d, off):
+    """Upstream g of either sign, exact zeros, and the two device scalars (incoming d loss, weight normalisation)
+    multiplied in by the kernels: the statistics-in-the-MMA backward carries |g| in the exponent and the signs
+    separately (row sign in the dU pass, per-user sign words in the dV pass)."""
+    from two_tower_models_b200 import ops
+
+    U, V = _ce_inputs(B, N, d, 3 * B + N + d)
+    gen = torch.Generator().manual_seed(11)
+    g = (torch.rand(B, generator=gen) - 0.4) / B
+    g[::7] = 0.0
+    s1, s2 = torch.tensor([-1.7]), torch.tensor([0.35])
+    _, lse_ref = oracle.inbatch_ce(U.double(), V.double(), off)
+    dU_ref, dV_ref = oracle.inbatch_ce_backward(U.double(), V.double(), lse_ref, (g * s1 * s2).double(), off)
+    dev = _dev()
+    dU, dV, dU16, dV16 = ops.inbatch_ce_backward_raw(
+        ops.cast_rows_bf16(U.to(dev)), ops.cast_rows_bf16(V.to(dev)), B, N, d, off,
+        lse_ref.float().to(dev), g.to(dev), g_scale=s1.to(dev), g_scale2=s2.to(dev))
+    torch.cuda.synchronize()
+    assert_close_fro(dU, dU_ref, rtol=4e-3, what="dU " + _report("dU", dU, dU_ref.float()))
+    assert_close_fro(dV, dV_ref, rtol=4e-3, what="dV " + _report("dV", dV, dV_ref.float()))
+    zero_rows = dU[::7].abs().max()
+    assert float(zero_rows) == 0.0, "rows with g = 0 must get an exactly zero dU"
+
+
 def test_inbatch_ce_autograd_function_matches_oracle_autograd():
     from two_tower_models_b200 import ops
 
@@ -257,3 +282,11 @@ def test_inbatch_ce_full_size_properties():
     assert float(col_sum) < 2e-3 * float(scale), (float(col_sum), float(scale))
     dU_ref, _ = oracle.inbatch_ce_backward(U[sl].double(), V.double(), lse_ref, torch.full((1024,), 1.0 / B, dtype=torch.float64), 3000)
     assert_close_fro(dU[sl], dU_ref, rtol=4e-3, what="dU slice")
+    # (4) a 512-item slice of dV against the definition  dV[sl] = dS[:, sl]^T U  (all 8192 users, fp64 on the host);
+    # the row statistics are the device's own lse, already pinned by (3)
+    csl = slice(5000, 5512)
+    lse64 = lse.cpu().double()
+    P = torch.exp(U.double() @ V[csl].double().t() - lse64[:, None])
+    P[torch.arange(5000, 5512), torch.arange(512)] -= 1.0
+    dV_ref = (P / B).t() @ U.double()
+    assert_close_fro(dV[csl], dV_ref, rtol=4e-3, what="dV slice")

@@ -197,6 +197,58 @@ def test_base_model_edge_cases():
     assert torch.isfinite(loss2) and m2.user_tower_arch.weight.grad is not None
 
 
+def test_labels_given_as_a_vector_follow_the_reference_broadcast():
+    """train/train.py:53-55 builds labels of shape [B] (not [B, T]); with T = 1 the reference's
+    `sum(labels * weights, dim=-1)` then collapses to ONE scalar for the whole batch and the loss is the plain
+    mean cross entropy.  The drop-in has to reproduce that quirk, not 'fix' it."""
+    d, F, B = 64, 32, 256
+    p = _random_base_params(d, d, F, F, 300, 300, seed=13)
+    uvw = torch.tensor([1.0])
+    batch = _random_batch(B, F, F, 300, 300, 1, seed=14)
+    batch["labels"] = batch["labels"].reshape(B)
+    ref_loss, ref_grads = oracle.base_train_forward_with_grads(p, uvw, batch)
+    m = _build_base(p, uvw)
+    loss, _, _ = _run(m, batch)
+    assert abs(float(loss) - float(ref_loss)) <= LOSS_RTOL * abs(float(ref_loss))
+    for k, prm in m.named_parameters():
+        assert_close_fro(prm.grad, ref_grads[k], rtol=GRAD_RTOL, atol=BIAS_ATOL if prm.dim() == 1 else GRAD_ATOL, what=k)
+
+
+def test_overridden_tower_methods_are_dispatched_in_training():
+    """The reference's train_forward (:380-386) calls self.compute_user_embedding / self.compute_item_embeddings; a
+    subclass that overrides either one must see its override used in TRAINING too (not only in forward())."""
+    import two_tower_models_b200 as tt
+
+    d, F, B = 64, 32, 256
+    p = _random_base_params(d, d, F, F, 300, 300, seed=15)
+    calls = {"item": 0, "user": 0}
+
+    class Scaled(tt.TwoTowerBaseRetrieval):
+        def compute_item_embeddings(self, item_id, item_features):
+            calls["item"] += 1
+            return super().compute_item_embeddings(item_id, item_features) * 0.5
+
+        def compute_user_embedding(self, user_id, user_features, user_history):
+            calls["user"] += 1
+            return super().compute_user_embedding(user_id, user_features, user_history)
+
+    m = Scaled(10, 300, d, F, 300, d, F, [1.0], tt.BaselineMIPSModule(corpus_size=64, embedding_dim=d))
+    m.load_state_dict(p, strict=True)
+    m = m.cuda()
+    batch = _random_batch(B, F, F, 300, 300, 1, seed=16)
+    b = {k: v.cuda() for k, v in batch.items()}
+    loss = m.train_forward(b["user_id"], b["user_features"], b["user_history"], b["item_id"], b["item_features"],
+                           b["position"], b["labels"])
+    loss.backward()
+    assert calls == {"item": 1, "user": 1}
+    # oracle with the item tower's output halved = the same model with the item tower Linear scaled by 0.5
+    p2 = {k: v.clone() for k, v in p.items()}
+    p2["item_tower_arch.weight"] *= 0.5
+    p2["item_tower_arch.bias"] *= 0.5
+    ref = oracle.base_train_forward(p2, torch.tensor([1.0]), batch)
+    assert abs(float(loss) - float(ref)) <= LOSS_RTOL * abs(float(ref))
+
+
 def test_requires_cuda_and_library():
     import two_tower_models_b200 as tt
 

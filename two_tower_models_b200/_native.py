@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
+# TT_B200_LIB selects another build of the same sources (bring-up builds with extra -D flags); never a fallback
+LIB_PATH = os.environ.get("TT_B200_LIB") or os.path.join(_HERE, "csrc", "libtt_b200.so")
 
 _lib = None
 

@@ -13,9 +13,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "gemm.cu", "ce.cu", "ce_bwd2.cu", "elementwise.cu", "mips.cu", "attn.cu", "attn_tc.cu", "tower.cu", "tower_bwd.cu"]  # missing files are skipped
+SOURCES = ["api.cu", "gemm.cu", "ce.cu", "ce_bwd2.cu", "ce_bwd3.cu", "elementwise.cu", "mips.cu", "attn.cu", "attn_tc.cu", "tower.cu", "tower_bwd.cu"]  # missing files are skipped
 HEADERS = ["common.cuh", "ce_common.cuh", "kernels.h", os.path.join(ROOT, "include", "tt_b200.h")]
-LIB = os.path.join(HERE, "libtt_b200.so")
+LIB = os.environ.get("TT_B200_LIB_OUT") or os.path.join(HERE, "libtt_b200.so")  # bring-up builds go to another file
+VARIANT = os.path.splitext(os.path.basename(LIB))[0]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -23,6 +24,8 @@ FLAGS = [
 ]
 if os.environ.get("TT_CE_BWD_LEAN") == "1":  # candidate epilogue of the CE backward (ce_bwd2.cu), not yet measured
     FLAGS.append("-DTT_CE_BWD_LEAN")
+if os.environ.get("TT_CE_POLY") == "1":  # every fourth exponential of the v3 CE backward on the FMA pipe (ce_bwd3.cu)
+    FLAGS.append("-DTT_CE_POLY")
 if os.environ.get("TT_CE_BRINGUP") == "1":  # clock64 timelines / partial epilogues of the CE kernels (tools/trace_ce.py)
     FLAGS.append("-DTT_CE_BRINGUP")
 
@@ -39,14 +42,14 @@ def _digest(paths):
 def build(force=False, verbose=False):
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
     hdrs = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
-    stamp = os.path.join(HERE, ".build_stamp")
+    stamp = os.path.join(HERE, ".build_stamp" + ("" if VARIANT == "libtt_b200" else "." + VARIANT))
     dig = _digest(srcs + hdrs)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     objs = []
 
     def compile_one(src):
-        obj = src[:-3] + ".o"
+        obj = src[:-3] + ("" if VARIANT == "libtt_b200" else "." + VARIANT) + ".o"
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
@@ -61,7 +64,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    with open(os.path.join(HERE, "ptxas_report.txt"), "w") as f:
+    with open(os.path.join(HERE, "ptxas_report.txt" if VARIANT == "libtt_b200" else "ptxas_report." + VARIANT + ".txt"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))

@@ -514,15 +514,34 @@ static size_t fwd_ws_bytes(const Sched& s, long long Bpad) {
 }
 static size_t bwd_ws_bytes(const Sched& s, int DP) { return (size_t)s.max_slots * s.XT * 128 * DP * sizeof(float); }
 
-size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d) {
+// v3 backward kernels (ce_bwd3.cu, d <= 128) unless TT_CE_BWD_V3=0
+static bool use_bwd_v3() {
+  static const bool on = !(getenv("TT_CE_BWD_V3") && atoi(getenv("TT_CE_BWD_V3")) == 0);
+  return on;
+}
+// columns of Y per score tile of the backward kernels
+static int bwd_tile_cols(int DP, bool v3) { return (v3 && DP <= 128) ? ce_bwd3_tile_cols(DP) : (DP == 256 ? 64 : 128); }
+
+// forward / backward partials (sized for either backward kernel generation); the v3 backward's ext block (bias rows +
+// sign words of the users) follows at this offset
+static size_t ce_ws_base(long long B, long long N, long long d) {
   const int DP = pick_dp(d);
-  const int BNb = DP == 256 ? 64 : 128;
   const long long Bpad = (B + 127) / 128 * 128;
-  size_t a = fwd_ws_bytes(make_sched(B, N, 128), Bpad);
-  size_t b = bwd_ws_bytes(make_sched(B, N, BNb), DP);
-  size_t c = bwd_ws_bytes(make_sched(N, B, BNb), DP);
-  const size_t bw = (b + 255) / 256 * 256 + c;  // the two backward passes use disjoint regions
-  return (a > bw ? a : bw) + 256;
+  size_t best = fwd_ws_bytes(make_sched(B, N, 128), Bpad);
+  size_t bmax = 0, cmax = 0;  // the two backward passes use disjoint regions: [dU partials | dV partials]
+  for (int v3 = 0; v3 < 2; ++v3) {
+    const int BNb = bwd_tile_cols(DP, v3 != 0);
+    const size_t b = (bwd_ws_bytes(make_sched(B, N, BNb), DP) + 255) / 256 * 256;
+    const size_t c = bwd_ws_bytes(make_sched(N, B, BNb), DP);
+    if (b > bmax) bmax = b;
+    if (c > cmax) cmax = c;
+  }
+  if (bmax + cmax > best) best = bmax + cmax;
+  return (best + 256 + 255) / 256 * 256;
+}
+
+size_t inbatch_ce_workspace_bytes(long long B, long long N, long long d) {
+  return ce_ws_base(B, N, d) + ce_bwd3_ext_bytes(B);
 }
 
 template <int DP>
@@ -699,8 +718,9 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
                        long long yr, long long d, long long diag_shift, const float* g, const float* g_scale,
                        const float* g_scale2, const float* lse, float* out32,
                        long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
-                       ReduceJob& job, cudaStream_t stream) {
-  constexpr int BN = DP == 256 ? 64 : 128;
+                       ReduceJob& job, cudaStream_t stream, const void* ext = nullptr) {
+  const bool v3 = ext != nullptr && DP <= 128 && (nyp == 1 || ce_bwd3_tile_cols(DP) == 128);  // (96-row tiles would straddle parts)
+  const int BN = bwd_tile_cols(DP, v3);
   const Sched s = make_sched(xr, yr, BN);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
   CeBwdArgs a;
@@ -720,7 +740,16 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
   if (rc) return rc;
   rc = make_tmap_set(&ty, Yp, nyp, y_rows_per_part, yr, d, ldy, BN);
   if (rc) return rc;
-  rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
+  if (v3) {  // statistics inside the score MMA (ce_bwd3.cu)
+    CeBwd3Args b;
+    b.XR = a.XR; b.YR = a.YR; b.diag_shift = a.diag_shift; b.T = a.T; b.total = a.total; b.CT = a.CT;
+    b.g = g; b.g_scale = g_scale; b.g_scale2 = g_scale2; b.lse = lse; b.signmask = nullptr;
+    b.partial = a.partial; b.slot_stride = a.slot_stride; b.trace = a.trace; b.cta_times = a.cta_times;
+    b.trace_cta = getenv("TT_CE_TRACE_CTA") ? atoi(getenv("TT_CE_TRACE_CTA")) : 0;
+    rc = launch_ce_bwd3(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream);
+  } else {
+    rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
+  }
   if (rc) return rc;
   job.rows = (int)xr; job.d = (int)d; job.CT = s.CT; job.T = s.T; job.slot_stride = a.slot_stride;
   job.partial = a.partial; job.out32 = out32; job.ld32 = ld32; job.out16 = (bf16*)out16; job.ld16 = ld16;
@@ -748,23 +777,37 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
   TT_CHECK(d <= 256, "inbatch_ce_bwd: embedding dim %lld > 256 is not supported", d);
   TT_CHECK((ldu % 8) == 0 && (ldv % 8) == 0 && ((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0,
            "inbatch_ce_bwd: operands need 16-byte aligned rows");
-  TT_CHECK(ws_bytes >= inbatch_ce_workspace_bytes(B, N, d) - 256, "inbatch_ce_bwd: workspace too small");
+  TT_CHECK(ws_bytes >= inbatch_ce_workspace_bytes(B, N, d), "inbatch_ce_bwd: workspace too small");
   const int DP = pick_dp(d);
-  const int BNb = DP == 256 ? 64 : 128;
-  const size_t offB = (bwd_ws_bytes(make_sched(B, N, BNb), DP) + 255) / 256 * 256;  // region of the dV pass
+  const bool v3 = use_bwd_v3() && DP <= 128;
+  size_t offB = 0;  // region of the dV pass: behind the larger of the two possible dU geometries
+  for (int k = 0; k < 2; ++k) {
+    const size_t o = (bwd_ws_bytes(make_sched(B, N, bwd_tile_cols(DP, k != 0)), DP) + 255) / 256 * 256;
+    if (o > offB) offB = o;
+  }
   ReduceJob ja, jb;
   ja.blocks = jb.blocks = 0;
   ja.rows = jb.rows = 0;
   int rc = 0;
   const bool wantU = dU || dU16, wantV = dV || dV16;
+  // v3 kernels: one small launch turns (g, lse) into the users' bias rows + sign words for the dV pass
+  void* ext = nullptr;
+  if (v3 && (wantU || wantV)) {
+    ext = (char*)ws + ce_ws_base(B, N, d);
+    TT_CHECK(ws_bytes >= ce_ws_base(B, N, d) + ce_bwd3_ext_bytes(B), "inbatch_ce_bwd: workspace too small for the ext block");
+    if (wantV) {
+      rc = ce_bwd3_prep(B, g, lse, ext, stream);
+      if (rc) return rc;
+    }
+  }
 #define TT_PASS(DPV)                                                                                                 \
   do {                                                                                                               \
     if (wantU)                                                                                                       \
       rc = ce_bwd_pass<DPV>(false, &U, 1, B, ldu, B, Vp, np, rows_per_part, ldv, N, d, target_offset, g, g_scale, g_scale2, lse, dU, lddu, dU16, \
-                            lddu16, dU_colsum, ws, offB, ja, stream);                                                \
+                            lddu16, dU_colsum, ws, offB, ja, stream, ext);                                           \
     if (rc == 0 && wantV)                                                                                            \
       rc = ce_bwd_pass<DPV>(true, Vp, np, rows_per_part, ldv, N, &U, 1, B, ldu, B, d, -target_offset, g, g_scale, g_scale2, lse, dV, lddv, dV16, \
-                            lddv16, dV_colsum, (char*)ws + offB, ws_bytes - offB, jb, stream);                       \
+                            lddv16, dV_colsum, (char*)ws + offB, ws_bytes - offB, jb, stream, ext);                  \
   } while (0)
   if (DP == 64) TT_PASS(64);
   else if (DP == 128) TT_PASS(128);

@@ -77,4 +77,28 @@ struct CeBwdArgs {
 int launch_ce_bwd2(int DP, bool colstats, const TmapSet& tx, const TmapSet& ty, const CeBwdArgs& a, int grid,
                    cudaStream_t st);
 
+// v3 backward kernel (ce_bwd3.cu, d <= 128): statistics folded into the score MMA, E in place, 16 epilogue warps
+struct CeBwd3Args {
+  int XR, YR;
+  long long diag_shift;
+  long long T, total;
+  int CT;
+  const float* g;            // upstream dL/dce, indexed by user (any sign)
+  const float* g_scale;      // optional device scalars multiplied into g, or null
+  const float* g_scale2;
+  const float* lse;          // indexed by user
+  const uint32_t* signmask;  // sign bits of g, 32 users per word (set by launch_ce_bwd3 from the ext block)
+  float* partial;            // [max_slots][XT*128][DP]
+  long long slot_stride;
+  long long* trace;               // bring-up builds only (TT_CE_BRINGUP)
+  unsigned long long* cta_times;
+  int trace_cta;                  // CTA whose clock64 timeline is recorded (TT_CE_TRACE_CTA)
+};
+// bytes of the per-launch "ext" block: [users_pad, 64] bf16 bias rows + sign words; filled by ce_bwd3_prep
+int ce_bwd3_tile_cols(int DP);  // columns of Y per score tile (128 at d <= 64, 96 at d <= 128)
+size_t ce_bwd3_ext_bytes(long long users);
+int ce_bwd3_prep(long long users, const float* g, const float* lse, void* ext, cudaStream_t st);
+int launch_ce_bwd3(int DP, bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext,
+                   CeBwd3Args a, int grid, cudaStream_t st);
+
 }  // namespace tt

@@ -96,6 +96,19 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t p
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+// Non-blocking probe of a phase (no suspension): issued EARLY, consumed after other work, it hides the ~100-cycle
+// latency of a barrier read behind that work; `mbar_wait_probed` falls back to the blocking wait when it failed.
+__device__ __forceinline__ uint32_t mbar_probe(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU box.
 #ifndef TT_MBAR_TIMEOUT_CYCLES
 #define TT_MBAR_TIMEOUT_CYCLES (6000000000LL)  // ~3 s at 2 GHz
@@ -112,6 +125,9 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parit
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_wait_probed(uint64_t* bar, uint32_t parity, uint32_t probe_ok) {
+  if (!probe_ok) mbar_wait_addr(smem_u32(bar), parity);
+}
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -220,6 +236,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -31,7 +31,7 @@ class _CudaKernels:
 
     @staticmethod
     def operand(x: torch.Tensor) -> torch.Tensor:
-        x16 = getattr(x, "_tt_bf16", None)
+        x16 = ops.shadow_of(x)
         return x16 if x16 is not None else ops.cast_rows_bf16(ops._f32c(x))
 
     @staticmethod
@@ -41,7 +41,7 @@ class _CudaKernels:
     @staticmethod
     def ce_backward(U_op, V_op, B, N, d, offset, lse, g):
         dU, dV, dU16, _ = ops.inbatch_ce_backward_raw(U_op, V_op, B, N, d, offset, lse, g)
-        dU._tt_bf16 = dU16
+        ops.attach_shadow(dU, dU16)
         return dU, dV
 
 

@@ -111,6 +111,26 @@ def _i64c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def attach_shadow(t: torch.Tensor, t16: Optional[torch.Tensor], colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Attach the bf16 operand copy (and optionally the fp32 column sums) of `t` as attributes, stamped with the
+    tensor's (data_ptr, version): a consumer only trusts them while `t` is still the very tensor they describe
+    (autograd may accumulate another gradient into it in place, which bumps the version)."""
+    if t16 is not None:
+        t._tt_bf16 = t16
+    if colsum is not None:
+        t._tt_colsum = colsum
+    t._tt_stamp = (t.data_ptr(), t._version)
+    return t
+
+
+def shadow_of(t: torch.Tensor, name: str = "_tt_bf16") -> Optional[torch.Tensor]:
+    """The attribute attached by attach_shadow, or None when it is absent or stale."""
+    s = getattr(t, name, None)
+    if s is None or getattr(t, "_tt_stamp", None) != (t.data_ptr(), t._version):
+        return None
+    return s
+
+
 # --------------------------------------------------------------------------------------------
 # raw ops
 # --------------------------------------------------------------------------------------------
@@ -350,15 +370,14 @@ class TowerFunction(torch.autograd.Function):
         ctx.need_dfeats = feats.requires_grad
         ctx.has_extra = extra is not None
         ctx.row_exchange = row_exchange
-        emb._tt_bf16 = emb16
-        return emb
+        return attach_shadow(emb, emb16)
 
     @staticmethod
     def backward(ctx, demb):
         ids, feats16, H16, X16, w0_16, w1_16, wt_16 = ctx.saved_tensors
         B, F, D, DI, E, D8, KT, table_rows = ctx.dims
         dev = demb.device
-        demb16 = getattr(demb, "_tt_bf16", None)
+        demb16 = shadow_of(demb)
         if demb16 is None:
             demb16 = cast_rows_bf16(_f32c(demb))
         hid = H16.shape[1]
@@ -459,14 +478,13 @@ class LinearFunction(torch.autograd.Function):
         ctx.dims = (B, K, N)
         ctx.has_bias = b is not None
         ctx.need_dx = x.requires_grad
-        y._tt_bf16 = y16
-        return y
+        return attach_shadow(y, y16)
 
     @staticmethod
     def backward(ctx, dy):
         x16, w16 = ctx.saved_tensors
         B, K, N = ctx.dims
-        dy16 = getattr(dy, "_tt_bf16", None)
+        dy16 = shadow_of(dy)
         if dy16 is None:
             dy16 = cast_rows_bf16(_f32c(dy))
         dW = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
@@ -534,8 +552,8 @@ class InBatchCEFunction(torch.autograd.Function):
         N = V.shape[0]
         if V.shape[1] != d:
             raise RuntimeError(f"user/item embedding dims differ: {d} vs {V.shape[1]}")
-        U16 = getattr(U, "_tt_bf16", None)
-        V16 = getattr(V, "_tt_bf16", None)
+        U16 = shadow_of(U)
+        V16 = shadow_of(V)
         if U16 is None:
             U16 = cast_rows_bf16(_f32c(U))
         if V16 is None:
@@ -551,11 +569,9 @@ class InBatchCEFunction(torch.autograd.Function):
         B, N, d, off = ctx.dims
         cs = torch.zeros((2, d), dtype=torch.float32, device=g.device) if d <= 128 else None
         dU, dV, dU16, dV16 = inbatch_ce_backward_raw(U16, V16, B, N, d, off, lse, _f32c(g), colsums=cs)
-        dU._tt_bf16 = dU16
-        dV._tt_bf16 = dV16
-        if cs is not None:  # fp32 column sums = bias gradients of the tower Linears, saves two reduction launches
-            dU._tt_colsum = cs[0]
-            dV._tt_colsum = cs[1]
+        # fp32 column sums = bias gradients of the tower Linears, saves two reduction launches
+        attach_shadow(dU, dU16, None if cs is None else cs[0])
+        attach_shadow(dV, dV16, None if cs is None else cs[1])
         return dU, dV, None
 
 
@@ -575,16 +591,17 @@ class InBatchWeightedLossFunction(torch.autograd.Function):
         N = V.shape[0]
         if V.shape[1] != d:
             raise RuntimeError(f"user/item embedding dims differ: {d} vs {V.shape[1]}")
-        U16 = getattr(U, "_tt_bf16", None)
-        V16 = getattr(V, "_tt_bf16", None)
+        U16 = shadow_of(U)
+        V16 = shadow_of(V)
         if U16 is None:
             U16 = cast_rows_bf16(_f32c(U))
         if V16 is None:
             V16 = cast_rows_bf16(_f32c(V))
         labels, weights = _f32c(labels), _f32c(weights)
         dev = U16.device
-        out = torch.empty(3 * B + 2, dtype=torch.float32, device=dev)  # ce | lse | g | loss | g_norm
-        ce, lse, g, loss, g_norm = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:3 * B + 1].view(()), out[3 * B + 1:]
+        out = torch.empty(3 * B + 1, dtype=torch.float32, device=dev)  # ce | lse | g | g_norm (saved for backward)
+        ce, lse, g, g_norm = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:]
+        loss = torch.empty((), dtype=torch.float32, device=dev)  # its own storage: the caller may modify it in place
         ws = _ce_workspace(B, N, d, dev)
         with _span("inbatch_ce_fwd"):
             _native.check(
@@ -605,11 +622,8 @@ class InBatchWeightedLossFunction(torch.autograd.Function):
         cs = torch.zeros((2, d), dtype=torch.float32, device=g.device) if d <= 128 else None
         dU, dV, dU16, dV16 = inbatch_ce_backward_raw(U16, V16, B, N, d, 0, lse, g, colsums=cs,
                                                      g_scale=_f32c(dloss).reshape(1), g_scale2=g_norm)
-        dU._tt_bf16 = dU16
-        dV._tt_bf16 = dV16
-        if cs is not None:
-            dU._tt_colsum = cs[0]
-            dV._tt_colsum = cs[1]
+        attach_shadow(dU, dU16, None if cs is None else cs[0])
+        attach_shadow(dV, dV16, None if cs is None else cs[1])
         return dU, dV, None, None
 
 
@@ -650,7 +664,7 @@ def mips_topk(query: torch.Tensor, corpus: torch.Tensor, corpus16: torch.Tensor,
     c32 = _f32c(corpus)
     nq, d = q32.shape
     nc = c32.shape[0]
-    q16 = getattr(query, "_tt_bf16", None)
+    q16 = shadow_of(query)
     if q16 is None:
         q16 = cast_rows_bf16(q32)
     L = _native.lib()
@@ -1048,8 +1062,7 @@ class TowerSetFunction(torch.autograd.Function):
         ctx.tw = tw
         outs = []
         for d in tw:
-            d["emb"]._tt_bf16 = d["emb16"]
-            outs.append(d["emb"])
+            outs.append(attach_shadow(d["emb"], d["emb16"]))
         return tuple(outs)
 
     @staticmethod
@@ -1062,12 +1075,12 @@ class TowerSetFunction(torch.autograd.Function):
         for d, demb in zip(tw, dembs):
             if demb is None:  # this tower's embedding did not reach the loss
                 demb = torch.zeros_like(d["emb"])
-            d16 = getattr(demb, "_tt_bf16", None)
+            d16 = shadow_of(demb)
             demb = _f32c(demb)
             if d16 is None:
                 d16 = torch.empty((d["B"], _r8(d["DI"])), dtype=_BF16, device=dev)
                 casts.append((demb, 0, d["DI"], d16, 0, _r8(d["DI"])))
-            d["demb"], d["demb16"], d["demb_colsum"] = demb, d16, getattr(demb, "_tt_colsum", None)
+            d["demb"], d["demb16"], d["demb_colsum"] = demb, d16, shadow_of(demb, "_tt_colsum")
         if casts:
             cast_batched(casts)
         # every accumulated gradient of every tower lives in one zero-filled arena (one memset)
@@ -1201,7 +1214,5 @@ def inbatch_ce_backward_parts(U16, v_ptrs, rows_per_part, ldv, B, N, d, target_o
                 dV.data_ptr(), dV.stride(0), None, 0, _ptr(cs), None, ws.data_ptr(), ws.numel(), _stream()),
             "inbatch_ce_bwd_parts",
         )
-    dU._tt_bf16 = dU16
-    if cs is not None:
-        dU._tt_colsum = cs[0]
+    attach_shadow(dU, dU16, None if cs is None else cs[0])
     return dU, dV

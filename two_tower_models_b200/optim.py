@@ -75,4 +75,7 @@ class FusedAdam(torch.optim.Optimizer):
                 _native.check(L.tt_adam_step(arr, len(chunk), group["lr"], beta1, beta2, group["eps"],
                                              group["weight_decay"], step_dev.data_ptr(), ticket.data_ptr(), stream),
                               "adam_step")
+                # the kernel wrote the parameters through raw pointers: tell autograd (and the bf16 operand caches of
+                # ops.PackedWeights, which key on `_version`) that they changed
+                torch.autograd.graph.increment_version(chunk)
         return loss

@@ -194,7 +194,12 @@ class TwoTowerBaseRetrieval(nn.Module):
         stream (forked from / joined to the caller's stream; autograd replays the same split in backward):
         each tower is a chain of small launch-latency-bound kernels that fills half of the SMs at most.
         """
-        if _BATCH_TOWERS and item_id.is_cuda and self._fused_user_tower_ok():
+        cls = type(self)
+        base_towers = (cls.compute_user_embedding is TwoTowerBaseRetrieval.compute_user_embedding
+                       and cls.compute_item_embeddings is TwoTowerBaseRetrieval.compute_item_embeddings)
+        if _BATCH_TOWERS and item_id.is_cuda and self._fused_user_tower_ok() and base_towers:
+            # (a subclass that overrides compute_user_embedding / compute_item_embeddings is dispatched through its
+            # methods below, exactly as the reference's train_forward :380-386 does)
             # both towers advance in lock step: every stage is one launch covering the user and the item side
             fu, fi = self.user_features_arch, self.item_features_arch
             user_embedding, item_embeddings = ops.TowerSetFunction.apply(
@@ -215,7 +220,7 @@ class TwoTowerBaseRetrieval(nn.Module):
             user_embedding = self.compute_user_embedding(user_id, user_features, user_history)
             cur.wait_stream(side)
             item_embeddings.record_stream(cur)
-            shadow = getattr(item_embeddings, "_tt_bf16", None)
+            shadow = ops.shadow_of(item_embeddings)
             if shadow is not None:
                 shadow.record_stream(cur)
         else:
