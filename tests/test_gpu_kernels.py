@@ -170,6 +170,8 @@ CE_CASES = [
     (200, 456, 256, 101),
     (1024, 1024, 256, 0),
     (2048, 2048, 128, 0),
+    (128, 32768, 128, 4096),  # few users against many (all-gathered) items: the dV pass walks several row tiles per CTA
+    (4096, 160, 64, 0) if False else (96, 20000, 64, 77),
 ]
 
 

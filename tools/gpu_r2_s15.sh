@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+C=$PWD/two_tower_models_b200/csrc
+echo "== kernels parity (v3 default)"
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider --timeout 600 -x > $O/s15_kernels.txt 2>&1; echo "rc=$?"; tail -15 $O/s15_kernels.txt
+for i in 1 2 3; do echo "== ce_time v3"; timeout 300 python tools/ce_time.py 64 128 2>&1 | tee -a $O/s15_ce_time_v3.txt | tail -2; done
+echo "== trace dU v3 CTA 2"; TT_CE_TRACE_CTA=2 TT_B200_LIB=$C/libtt_b200_bringup.so timeout 300 python tools/trace_ce.py 128 > $O/s15_trace_dU.txt 2>&1; head -8 $O/s15_trace_dU.txt | cut -c1-200; tail -4 $O/s15_trace_dU.txt
+echo "== trace dV v3 CTA 2"; TT_CE_TRACE_CTA=2 TT_B200_LIB=$C/libtt_b200_bringup.so timeout 300 python tools/trace_ce.py 128 dv > $O/s15_trace_dV.txt 2>&1; head -8 $O/s15_trace_dV.txt | cut -c1-200; tail -4 $O/s15_trace_dV.txt
+echo "== models parity"
+timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_debias.py -m gpu -q -p no:cacheprovider --timeout 600 > $O/s15_models.txt 2>&1; echo "rc=$?"; tail -5 $O/s15_models.txt
+echo "== step breakdown"; timeout 300 python tools/step_breakdown.py 2>&1 | grep -v -i "warn\|return Variable" | tail -6 | tee $O/s15_breakdown.txt

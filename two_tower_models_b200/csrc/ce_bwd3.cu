@@ -12,19 +12,16 @@
 //     E = exp2(S' log2e + log2|g_scale|) for both passes: no per-row / per-column statistics, no multiply by g.
 //     Signs: the sign of g_scale and (dU) of the row's g are XORed onto the packed bf16 pairs; (dV) a per-user sign
 //     bitmask is applied to a 32-column chunk only when it is non-zero (never, with the clamped label weights).
-//   * E is written IN PLACE over the first half of the score columns it was computed from (bf16 pairs), and is the
-//     TMEM A operand of  acc += E Y  from there.  tcgen05.mma executes in issue order, so the next S = X Y^T into that
-//     buffer simply follows the E Y that read it: the s_empty / e_empty barriers of v2 are gone, the freed columns
-//     hold the X tile and its bias step.
-//   * THREE score buffers.  A buffer's life is a dependent chain  epilogue(t) -> acc += E(t) Y(t) -> S(t + NB) ->
-//     epilogue(t + NB)  of ~D + 1100 + hand-shakes cycles (D ~ 1400: the warps of a scheduler all start on the same
-//     barrier and run their MUFU phases in lock step); with two 128-column buffers that chain, not a pipe, set the pace
-//     (1700 cycles per tile measured, profiles/r02_ce_bwd_v3a_timeline.txt).  TMEM has room for three buffers only at
-//     96 columns (d = 128: 3 x 96 + 128 acc + 64 X + 8 bias = 488), so the score tiles are 128 x 96 there.
+//   * Two score buffers, released as soon as their values sit in registers, and two separate E buffers (bf16 pairs, the
+//     TMEM A operand of  acc += E Y).  Earlier drafts kept E in place in the score buffer (two or three buffers): then
+//     S(t + NB) has to wait for the COMPLETION of acc += E(t) Y(t), which the in-order tensor queue places right behind
+//     S(t + NB - 1) - the pipe ran S, E Y, ~350 idle cycles of completion -> barrier -> wake-up -> issue, per tile
+//     (profiles/r02_ce_bwd_v3_timelines.md).  With E elsewhere the score MMAs only wait for a tmem load.
+//     TMEM (d = 128): 2 x 96 S + 2 x 48 E + 128 acc + 64 X + 8 bias step = 488 columns, hence 128 x 96 score tiles.
 //   * BN / 32 column groups x 4 lane quarters of epilogue warps, 32 columns per thread and tile; the next segment's X
 //     tile is staged into TMEM before the finished accumulator is drained.
 //
-// TMEM columns: S/E buffers [0, NB*BN) | acc [.., +DP) | X [.., +DP/2) | X bias step [.., +8).
+// TMEM columns: S buffers [0, NB*BN) | E buffers [.., +NE*BN/2) | acc [.., +DP) | X [.., +DP/2) | X bias step [.., +8).
 // Warp roles: 0 .. 4 EG - 1 epilogue (group e = warp / 4 owns columns [32e, 32e+32) of every score tile, q = warp % 4 the
 // TMEM lane quarter), then TMA, UMMA issue of S = X Y^T, TMEM alloc, UMMA issue of acc += E Y (warp-uniform, elected lane).
 #include <stdlib.h>
@@ -35,17 +32,24 @@ namespace tt {
 
 namespace {
 
+#ifndef TT_CE3_CW
+#define TT_CE3_CW 32
+#endif
+
 template <int DP>
 struct Tile3 {
-  static constexpr int BN = DP == 64 ? 128 : 96;  // score-tile width (columns of Y per tile)
-  static constexpr int NB = 3;                    // score buffers in flight
+  static constexpr int BN = DP == 64 ? 128 : 96;  // score-tile width (columns of Y per tile); TMEM: 2 BN + BN + DP + DP/2 + 8 <= 512
+  static constexpr int NB = 2;                    // score buffers (free again once loaded into registers)
+  static constexpr int NE = 2;                    // E buffers (free again once acc += E Y has completed)
 };
 
 template <int DP, bool BIAS_X>
 struct Cfg3 {
   static constexpr int BN = Tile3<DP>::BN;
   static constexpr int NB = Tile3<DP>::NB;
-  static constexpr int EG = BN / 32;                                // epilogue column groups (4 warps each)
+  static constexpr int NE = Tile3<DP>::NE;
+  static constexpr int CW = TT_CE3_CW;                              // score columns per epilogue thread and tile (16 or 32)
+  static constexpr int EG = BN / CW;                                // epilogue column groups (4 warps each)
   static constexpr int THREADS = 128 + EG * 128;
   static constexpr int XP = DP / 32;                                // 32-column parts of the X tile / accumulator
   static constexpr int KBOX = DP / 64;
@@ -54,9 +58,10 @@ struct Cfg3 {
   static constexpr int Y_MAIN = BN * DP * 2;
   static constexpr int Y_BYTES = Y_MAIN + (BIAS_X ? 0 : EXT_BYTES);  // dV: the users' bias step travels with the Y tile
   static constexpr int ONES_BYTES = BIAS_X ? 128 * 128 : 0;          // dU: constant ones tile on the item side
-  static constexpr int STAGES = BIAS_X ? (DP == 64 ? 8 : 6) : 5;
+  static constexpr int STAGES = BIAS_X ? (DP == 64 ? 8 : 6) : (DP == 64 ? 5 : 5);
   static constexpr int SMEM_BYTES = X_BYTES + ONES_BYTES + STAGES * Y_BYTES + 1024 + 512;
-  static constexpr int ACC_COL = NB * BN;
+  static constexpr int E_COL = NB * BN;
+  static constexpr int ACC_COL = E_COL + NE * (BN / 2);
   static constexpr int X_COL = ACC_COL + DP;
   static constexpr int XE_COL = X_COL + DP / 2;
   static_assert(XE_COL + 8 <= 512, "TMEM budget");
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(Cfg3<DP, BIAS_X>::THREADS, 1)
 ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ TmapSet tmy,
                const __grid_constant__ CUtensorMap tme, const CeBwd3Args a) {
   using Cfg = Cfg3<DP, BIAS_X>;
-  constexpr int BN = Cfg::BN, EG = Cfg::EG, NB = Cfg::NB;
+  constexpr int BN = Cfg::BN, EG = Cfg::EG, NB = Cfg::NB, NE = Cfg::NE, CW = Cfg::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sx = smem;
@@ -111,9 +116,11 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   uint64_t* xt_full = bars + 2;   // X tile and its bias step staged in TMEM (16 epilogue warps)
   uint64_t* acc_full = bars + 3;
   uint64_t* acc_empty = bars + 4;
+  uint64_t* sx_free = bars + 13;  // the epilogue warps are done using the X buffer as drain staging (one phase per segment)
   uint64_t* s_full = bars + 5;    // [NB]
-  uint64_t* e_full = bars + 8;    // [NB]: E of the whole tile is in place (all epilogue warps)
-  uint64_t* y_full = bars + 8 + NB;
+  uint64_t* s_empty = bars + 7;   // [NB]: every epilogue warp holds its part of the score tile in registers
+  uint64_t* e_full = bars + 9;    // [NE]: E of the whole tile is stored (all epilogue warps)
+  uint64_t* y_full = bars + 14;
   uint64_t* y_empty = y_full + Cfg::STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_empty + Cfg::STAGES);
 
@@ -135,8 +142,12 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     mbar_init(xt_full, 4 * EG);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4 * EG);
-    for (int i = 0; i < NB; ++i) mbar_init(&s_full[i], 1);
-    for (int i = 0; i < NB; ++i) mbar_init(&e_full[i], 4 * EG);
+    mbar_init(sx_free, 4 * EG);
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4 * EG);
+    }
+    for (int i = 0; i < NE; ++i) mbar_init(&e_full[i], 4 * EG);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 1);
@@ -167,6 +178,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       uint32_t phase = 0, xs = 0;
       while (it.next(r, j0, j1)) {
         mbar_wait(x_empty, (xs & 1) ^ 1);
+        if (xs >= 2) mbar_wait(sx_free, xs & 1);  // the drain of segment xs - 2 staged through the X buffer
         mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
         int xrow;
         const CUtensorMap* mx = tmap_of(tmx, r * 128, xrow);
@@ -189,12 +201,9 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
   } else if (warp == W_MMA) {
     // ---- issuer of the score tiles  S' = X Y^T (+ bias step) ----
     // One thread issuing BOTH contractions spends ~300 dependent instructions per tile on descriptors and barriers and
-    // cannot keep the tensor pipe fed (v3b/v3c timelines: 860 cycles of MMA per tile, 1220 per tile measured, the gaps
-    // are the issuer's own instruction latency).  The two contractions therefore have one issuing warp each, on
-    // different SM sub-partitions.  Ordering between them goes through completion barriers: S(t) may overwrite score
-    // buffer t % NB once  acc += E(t - NB) Y(t - NB)  has COMPLETED, which is exactly the event y_empty[(t - NB) % STAGES]
-    // tracks for the TMA producer.  Barriers are probed one batch ahead (non-blocking test_wait); in steady state every
-    // probe succeeds and the thread never blocks.
+    // cannot keep the tensor pipe fed, so the two contractions have one issuing warp each, on different SM
+    // sub-partitions.  Barriers are probed one batch ahead (non-blocking test_wait); in steady state every probe
+    // succeeds and the thread never blocks.
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);
     SegIter it(a.T, a.total, a.CT);
@@ -204,7 +213,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     const uint64_t dones = make_smem_desc_sw128(smem_u32(sones), 0, 1024);
     auto probe_next = [&](uint32_t t, uint32_t& y_ok, uint32_t& b_ok) {
       y_ok = mbar_probe(&y_full[t % Cfg::STAGES], (t / Cfg::STAGES) & 1);
-      b_ok = t < (uint32_t)NB ? 1u : mbar_probe(&y_empty[(t - NB) % Cfg::STAGES], ((t - NB) / Cfg::STAGES) & 1);
+      b_ok = mbar_probe(&s_empty[t % NB], ((t / NB) & 1) ^ 1);
     };
     uint32_t y_ok = 0, b_ok = 1;
     while (it.next(r, j0, j1)) {
@@ -214,7 +223,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         const uint32_t buf = t1 % NB, stage = t1 % Cfg::STAGES;
         if (leader) CE3_STAMP(4, t1, 0);
         mbar_wait_probed(&y_full[stage], (t1 / Cfg::STAGES) & 1, y_ok);
-        if (t1 >= (uint32_t)NB) mbar_wait_probed(&y_empty[(t1 - NB) % Cfg::STAGES], ((t1 - NB) / Cfg::STAGES) & 1, b_ok);
+        mbar_wait_probed(&s_empty[buf], ((t1 / NB) & 1) ^ 1, b_ok);
         tc_fence_after();
         if (leader) CE3_STAMP(0, t1, 0);
         probe_next(t1 + 1, y_ok, b_ok);
@@ -233,7 +242,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       ++xs;
     }
   } else if (warp == W_MMA2) {
-    // ---- issuer of  acc += E Y  (E in place in the score buffer, Y read MN-major) ----
+    // ---- issuer of  acc += E Y  (E from its TMEM buffer, Y read MN-major); its completion frees the Y stage and E buffer ----
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc2 = make_idesc_bf16(128, DP, 0, 1);
     SegIter it(a.T, a.total, a.CT);
@@ -243,17 +252,17 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     uint32_t e_ok = 0;
     while (it.next(r, j0, j1)) {
       for (int j = j0; j < j1; ++j, ++t2) {
-        const uint32_t buf = t2 % NB, stage = t2 % Cfg::STAGES;
+        const uint32_t buf = t2 % NE, stage = t2 % Cfg::STAGES;
         if (leader) CE3_STAMP(1, t2, 0);
-        mbar_wait_probed(&e_full[buf], (t2 / NB) & 1, e_ok);
+        mbar_wait_probed(&e_full[buf], (t2 / NE) & 1, e_ok);
         if (j == j0) mbar_wait(acc_empty, (xs & 1) ^ 1);
         tc_fence_after();
         if (leader) CE3_STAMP(5, t2, 0);
-        e_ok = mbar_probe(&e_full[(t2 + 1) % NB], ((t2 + 1) / NB) & 1);
+        e_ok = mbar_probe(&e_full[(t2 + 1) % NE], ((t2 + 1) / NE) & 1);
         const uint64_t dyt = desc_advance(dyt0, stage * Cfg::Y_BYTES);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k)  // K = 16 rows of the Y tile per instruction
-          umma_bf16_ta_w(tmem_base + Cfg::ACC_COL, tmem_base + buf * BN + (k >> 1) * 32 + (k & 1) * 8,
+          umma_bf16_ta_w(tmem_base + Cfg::ACC_COL, tmem_base + Cfg::E_COL + buf * (BN / 2) + k * 8,
                          desc_advance(dyt, k * 2048), idesc2, (j > j0 || k > 0) ? 1u : 0u, leader);
         if (leader) CE3_STAMP(5, t2, 1);
         umma_commit_w(&y_empty[stage], leader);
@@ -325,8 +334,8 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       const long long tgt = row + a.diag_shift;
       const bool haspos = row < a.XR && tgt >= 0 && tgt < a.YR;
       const int jd = haspos ? (int)(tgt / BN) : -1;                  // tile that holds this row's positive
-      const bool mine = haspos && (int)((tgt % BN) >> 5) == e;       // ... and it is in this group's 32 columns
-      const int od = haspos ? (int)((tgt % BN) & 31) : 0;
+      const bool mine = haspos && (int)((tgt % BN) / CW) == e;       // ... and it is in this group's CW columns
+      const int od = haspos ? (int)((tgt % BN) % CW) : 0;
       float sub = 0.f;
       uint32_t sgn_row = sgn_gs;
       if (BIAS_X) {
@@ -336,44 +345,56 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       } else if (mine) {
         sub = fabsf(__ldg(a.g + tgt)) * gabs;
       }
+      // (Issuing the tcgen05.ld of tile t + 1 before the exponentials of tile t - two register sets - was measured
+      // SLOWER: 1560 instead of 1050 cycles per tile, with spills at 128 registers.)
       for (int j = j0; j < j1; ++j, ++t) {
         const uint32_t buf = t % NB;
-        uint32_t cmask = 0u;
-        if (!BIAS_X) cmask = __ldg(a.signmask + j * EG + e);  // sign bits of g of this chunk's 32 users (columns)
+        uint32_t cmask = 0u;  // sign bits of g of this chunk's CW users (columns)
+        if (!BIAS_X) cmask = CW == 32 ? __ldg(a.signmask + j * (BN / 32) + e)
+                                      : (__ldg(a.signmask + j * (BN / 32) + (e >> 1)) >> ((e & 1) * 16)) & 0xffffu;
         mbar_wait(&s_full[buf], (t / NB) & 1);
         tc_fence_after();
         if (lane == 0 && e == 0) CE3_STAMP(q < 2 ? 2 + q : 4 + q, t, 0);  // rows 2, 3, 6, 7 of the trace: the four lane quarters
-        const uint32_t addr = lane_base + buf * BN + e * 32;
-        float v[32];
-        tmem_ld32(addr, v);
+        float v[CW];
+        if (CW == 32) tmem_ld32(lane_base + buf * BN + e * CW, v);
+        else tmem_ld16(lane_base + buf * BN + e * CW, v);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);  // the score buffer goes back to the issuer of S = X Y^T
 #ifdef TT_CE_POLY
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < CW; ++i) {
           const float x = fmaf(v[i], LOG2E, c0);
           v[i] = (i & 3) == 3 ? exp2_poly(x) : ex2f(x);
         }
 #else
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ex2f(fmaf(v[i], LOG2E, c0));
+        for (int i = 0; i < CW; ++i) v[i] = ex2f(fmaf(v[i], LOG2E, c0));
 #endif
         if (mine && j == jd) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] -= (i == od) ? sub : 0.f;
+          for (int i = 0; i < CW; ++i) v[i] -= (i == od) ? sub : 0.f;
         }
-        uint32_t p[16];
+        uint32_t p[CW / 2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) ^ sgn_row;
+        for (int i = 0; i < CW / 2; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]) ^ sgn_row;
         if (!BIAS_X && cmask != 0u) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
+          for (int i = 0; i < CW / 2; ++i)
             p[i] ^= (((cmask >> (2 * i)) & 1u) << 15) | (((cmask >> (2 * i + 1)) & 1u) << 31);
         }
-        tmem_st16(addr, p);  // in place over the first 16 of the 32 score columns just read
+        // E buffer t % NE is free once acc += E(t - NE) Y(t - NE) has completed = the event y_empty tracks for that tile
+        if (t >= (uint32_t)NE) {
+          mbar_wait(&y_empty[(t - NE) % Cfg::STAGES], ((t - NE) / Cfg::STAGES) & 1);
+          tc_fence_after();
+        }
+        if (CW == 32) tmem_st16(lane_base + Cfg::E_COL + (t % NE) * (BN / 2) + e * (CW / 2), p);
+        else tmem_st8(lane_base + Cfg::E_COL + (t % NE) * (BN / 2) + e * (CW / 2), p);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&e_full[buf]);
+        if (lane == 0) mbar_arrive(&e_full[t % NE]);
         if (lane == 0 && e == 0) CE3_STAMP(q < 2 ? 2 + q : 4 + q, t, 1);
       }
       // the next segment's X tile goes into tensor memory first (its first score MMAs then overlap the drain)
@@ -387,22 +408,60 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
       tc_fence_after();
       if (q == 0 && lane == 0 && e == 0 && have2) CE3_STAMP(2, 61, 0);
       {
+        // A thread holds 32 consecutive columns of ONE row; written straight to global memory every store instruction
+        // would touch 32 different 128-byte lines (the first drafts did: 4000 cycles per drain, and the flood of partial
+        // sectors delayed the TMA loads of the next segment).  Each warp transposes through a private slice of the X
+        // staging buffer (idle after stage_x): CHF floats of its 32 rows per round, written with an XOR swizzle,
+        // read back so that 4 (2) consecutive lanes cover 64 (32) contiguous bytes of a row.
+        constexpr int CHF = DP == 64 ? 8 : 16;          // floats of a row per round
+        constexpr int CPR = CHF / 4;                    // 16-byte chunks per row and round
+        constexpr int RPI = 32 / CPR;                   // rows per read-back instruction
+        static_assert(4 * (EG < Cfg::XP ? EG : Cfg::XP) * 32 * CHF * 4 <= Cfg::X_BYTES, "drain staging exceeds the X buffer");
         const int slot = (int)(blockIdx.x - ((long long)r * a.CT) / a.T);
-        float* dst = a.partial + (long long)slot * a.slot_stride + row * DP;
+        float* tile = a.partial + (long long)slot * a.slot_stride + ((long long)r * 128 + q * 32) * DP;  // row q*32 of the tile
+        uint8_t* wbuf = sx + warp * (32 * CHF * 4);
+        const uint32_t sw = CHF == 16 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+        int last_part = -1;
+#pragma unroll
+        for (int part = 0; part < Cfg::XP; ++part)
+          if (part % EG == e) last_part = part;
+        if (last_part < 0) {  // this warp has no accumulator columns to drain (d = 64: two of the four groups)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
 #pragma unroll
         for (int part = 0; part < Cfg::XP; ++part) {
           if (part % EG != e) continue;
           float w[32];
           tmem_ld32(lane_base + Cfg::ACC_COL + part * 32, w);
           tmem_wait_ld();
+          if (part == last_part) {  // the accumulator columns of this warp are in registers: hand them back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+          }
+          if (q == 0 && lane == 0 && e == 0 && have2) CE3_STAMP(3, part == last_part ? 61 : 60, 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(dst + part * 32 + 4 * i) = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          for (int round = 0; round < 32 / CHF; ++round) {
+#pragma unroll
+            for (int c = 0; c < CPR; ++c)
+              *reinterpret_cast<float4*>(wbuf + lane * (CHF * 4) + ((c ^ sw) << 4)) =
+                  make_float4(w[round * CHF + 4 * c], w[round * CHF + 4 * c + 1], w[round * CHF + 4 * c + 2], w[round * CHF + 4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 32 / RPI; ++k) {
+              const int rr = k * RPI + lane / CPR, c = lane % CPR;
+              const uint32_t swr = CHF == 16 ? ((rr >> 1) & 3) : ((rr >> 2) & 1);
+              const float4 val = *reinterpret_cast<const float4*>(wbuf + rr * (CHF * 4) + ((c ^ swr) << 4));
+              *reinterpret_cast<float4*>(tile + (long long)rr * DP + part * 32 + round * CHF + 4 * c) = val;
+            }
+            __syncwarp();
+          }
+          if (q == 0 && lane == 0 && e == 0 && have2) CE3_STAMP(3, part == last_part ? 61 : 60, 1);
         }
+        if (lane == 0) mbar_arrive(sx_free);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
       if (q == 0 && lane == 0 && e == 0 && have2) CE3_STAMP(2, 61, 1);
       r = r2; j0 = j02; j1 = j12; have = have2;
       ++xs;
