@@ -222,6 +222,17 @@ int tt_inbatch_ce_loss_fwd(const void* U_bf16, int64_t ldu, const void* V_bf16, 
                            int64_t d, int64_t target_offset, const float* labels, int64_t ld_labels,
                            const float* weights, int64_t T, float* ce, float* lse, float* loss, float* g, float* g_norm,
                            void* workspace, int64_t workspace_bytes, void* stream);
+/* Batch-sharded form of tt_inbatch_ce_loss_fwd (one process per GPU, local users against all-gathered items, positives at
+ * column row + target_offset): writes ce[B], lse[B], g[i] = nuv_i and stats[0..1] = (max_i nuv_i, sum_i ce_i nuv_i) of
+ * THIS rank (stats needs room for 4 floats; [2..3] are scratch).  The per-rank pairs are all-gathered by the caller and
+ * folded by tt_sharded_loss_finalize into *loss = sum_r s_r / (max_r m_r * global_rows) and *g_norm = 1 / (max * rows),
+ * the reference's batch-global max and mean (src/two_tower_base_retrieval.py:339-343) over the concatenated batch. */
+int tt_inbatch_ce_loss_fwd_sharded(const void* U_bf16, int64_t ldu, const void* V_bf16, int64_t ldv, int64_t B, int64_t N,
+                                   int64_t d, int64_t target_offset, const float* labels, int64_t ld_labels,
+                                   const float* weights, int64_t T, float* ce, float* lse, float* g, float* stats,
+                                   void* workspace, int64_t workspace_bytes, void* stream);
+int tt_sharded_loss_finalize(const float* stats_all, int32_t world, int64_t global_rows, float* loss, float* g_norm,
+                             void* stream);
 /* tt_inbatch_ce_bwd with g multiplied by the DEVICE scalars *g_scale and *g_scale2 (each may be NULL = 1): the
  * incoming gradient of the scalar loss and *g_norm above are applied inside the kernels instead of by separate
  * elementwise launches. */

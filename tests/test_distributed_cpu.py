@@ -16,6 +16,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+def _spawn_with_free_port(fn, make_args, nprocs=2, attempts=4):
+    """mp.spawn(fn, args=make_args(port)) on a free local port; the port can be taken between probing and binding
+    (EADDRINUSE on a busy box), so a failed rendezvous is retried on another port."""
+    last = None
+    for _ in range(attempts):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        try:
+            mp.spawn(fn, args=make_args(port), nprocs=nprocs, join=True)
+            return
+        except Exception as exc:  # noqa: BLE001 - only the address-in-use case is retried
+            last = exc
+            if "EADDRINUSE" not in str(exc) and "address already in use" not in str(exc).lower():
+                raise
+    raise last
+
 
 class OracleKernels:
     """CPU stand-ins with the kernel interface of distributed._CudaKernels (fp32, exact)."""
@@ -59,7 +77,36 @@ def _problem():
     return p, torch.tensor([1.0, 0.5]), batch
 
 
-def _worker(rank, world, port, out):
+class _HookedTowers(_Towers):
+    """Non-identity debias hook: position-dependent weights plus an additional loss that is a SUM over the batch (like
+    the reference's mse_loss(reduction="sum") in src/two_tower_with_position_debiased_weights.py:101-103) and depends
+    on a parameter and on the user embedding."""
+
+    def debias_net_user_value(self, net_user_value, position, user_embedding):
+        w = 1.0 / (1.0 + 0.1 * position.float())
+        est = user_embedding[:, 0] * self.p["user_tower_arch/bias"][0] + 0.3
+        return net_user_value * w + 0.05, torch.sum((est - net_user_value) ** 2)
+
+
+def _hooked_single_process(p, uvw, batch):
+    """The same model on the concatenated batch in one process (reference :279-347 with the hook above)."""
+    import oracle
+
+    m = _HookedTowers(p, uvw)
+    P = m.named()
+    u = oracle.base_user_embedding(P, batch["user_id"], batch["user_features"])
+    v = oracle.base_item_embedding(P, batch["item_id"], batch["item_features"])
+    ce, _ = oracle.inbatch_ce(u, v)
+    nuv = torch.sum(batch["labels"] * uvw, dim=-1)
+    nuv, aux = m.debias_net_user_value(nuv, batch["position"], u)
+    nuv = torch.clamp(nuv, min=0.000001)
+    nuv = nuv / torch.max(nuv)
+    loss = torch.mean(ce * nuv) + aux
+    loss.backward()
+    return loss.detach(), {k: t.grad for k, t in P.items()}
+
+
+def _worker(rank, world, port, out, hooked=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -71,7 +118,7 @@ def _worker(rank, world, port, out):
         n = batch["user_id"].shape[0] // world
         sl = slice(rank * n, (rank + 1) * n)
         loc = {k: v[sl] for k, v in batch.items()}
-        m = _Towers(p, uvw)
+        m = (_HookedTowers if hooked else _Towers)(p, uvw)
         ctx = ttd.enable_data_parallel(m, kernels=OracleKernels)
         P = m.named()
         u = oracle.base_user_embedding(P, loc["user_id"], loc["user_features"])
@@ -89,18 +136,29 @@ def test_sharded_loss_equals_single_process_reference(tmp_path):
     import oracle
     from helpers import assert_close_fro
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    _spawn_with_free_port(_worker, lambda port: (2, port, out))
     got = torch.load(out)
     p, uvw, batch = _problem()
     ref_loss, ref_grads = oracle.base_train_forward_with_grads(p, uvw, batch)
     assert abs(float(got["loss"]) - float(ref_loss)) <= 1e-6 * abs(float(ref_loss))
     for k, g in ref_grads.items():
         assert_close_fro(got["grads"][k], g, rtol=1e-5, atol=1e-7, what=k)  # atol: analytically-zero item-side biases
+
+
+def test_sharded_loss_with_a_debias_hook_and_additional_loss(tmp_path):
+    """The hook's additional loss is a sum over the batch: its gradient must NOT be divided by the world size, and the
+    reported value must be the global sum (distributed.py scaled it by 1 / world)."""
+    from helpers import assert_close_fro
+
+    out = str(tmp_path / "rank0.pt")
+    _spawn_with_free_port(_worker, lambda port: (2, port, out, True))
+    got = torch.load(out)
+    p, uvw, batch = _problem()
+    ref_loss, ref_grads = _hooked_single_process(p, uvw, batch)
+    assert abs(float(got["loss"]) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    for k, g in ref_grads.items():
+        assert_close_fro(got["grads"][k], g, rtol=1e-4, atol=1e-6, what=k)
 
 
 def test_requires_process_group():

@@ -109,6 +109,8 @@ SIGNATURES = {
                                        P, I64, P]),
     "tt_adam_step": (I32, [P, I32, c_double, c_double, c_double, F32, F32, P, P, P]),
     "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
+    "tt_inbatch_ce_loss_fwd_sharded": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, I64, P, I64, P, P, P, P, P, I64, P]),
+    "tt_sharded_loss_finalize": (I32, [P, I32, I64, P, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_history_gather_pool": (I32, [P, I64, I64, P, I64, I64, P, P, I64, P, I64, P, P]),

@@ -276,6 +276,18 @@ int tt_inbatch_ce_loss_fwd(const void* U, int64_t ldu, const void* V, int64_t ld
   return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, loss, g, g_norm,
                              ws, (size_t)ws_bytes, S(stream));
 }
+int tt_inbatch_ce_loss_fwd_sharded(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
+                                   int64_t target_offset, const float* labels, int64_t ldl, const float* weights, int64_t T,
+                                   float* ce, float* lse, float* g, float* stats, void* ws, int64_t ws_bytes, void* stream) {
+  TT_CHECK(labels != nullptr && weights != nullptr && g != nullptr && stats != nullptr, "tt_inbatch_ce_loss_fwd_sharded: null argument");
+  // the local loss / g_norm scalars are by-products nobody reads here: they land behind the two statistics
+  return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, stats + 2, g,
+                             stats + 3, ws, (size_t)ws_bytes, S(stream), stats);
+}
+int tt_sharded_loss_finalize(const float* stats_all, int32_t world, int64_t global_rows, float* loss, float* g_norm,
+                             void* stream) {
+  return sharded_loss_finalize(stats_all, world, global_rows, loss, g_norm, S(stream));
+}
 int tt_inbatch_ce_bwd_scaled(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
                              int64_t target_offset, const float* lse, const float* g, const float* g_scale,
                              const float* g_scale2, float* dU,

@@ -421,7 +421,7 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
                        const float* __restrict__ part_s, const DiagOperands dg, float* __restrict__ ce,
                        float* __restrict__ lse, const float* __restrict__ labels, long long ldl,
                        const float* __restrict__ uvw, int TL, float inv_rows, float* __restrict__ loss,
-                       float* __restrict__ g, float* __restrict__ g_norm, LossSync* sync) {
+                       float* __restrict__ g, float* __restrict__ g_norm, LossSync* sync, float* __restrict__ stats) {
   __shared__ float red_m[8], red_s[8];
   __shared__ float sdiag[COMBINE_RB];
   __shared__ unsigned int last;
@@ -483,12 +483,38 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
       const float gn = inv_rows / m;
       *loss = sm * gn;
       *g_norm = gn;
+      if (stats != nullptr) {  // batch-sharded loss: this rank's (max nuv, sum ce nuv), merged across ranks afterwards
+        stats[0] = m;
+        stats[1] = sm;
+      }
       sync->ticket = 0;  // ready for the next launch (CUDA-graph replay)
     }
   }
 }
 
 __global__ void set_scalar_kernel(float* p, float v) { *p = v; }
+
+// Batch-sharded loss: fold the all-gathered per-rank (max nuv, sum ce nuv) pairs into the global weighted mean
+// loss = sum_r s_r / (max_r m_r * rows) and the scalar g_norm = 1 / (max * rows) the backward kernels multiply into g.
+__global__ void sharded_loss_finalize_kernel(const float* __restrict__ stats_all, int world, float inv_rows,
+                                             float* __restrict__ loss, float* __restrict__ g_norm) {
+  float m = 0.f, sm = 0.f;
+  for (int r = 0; r < world; ++r) {  // fixed order: every rank computes bit-identical scalars
+    m = fmaxf(m, stats_all[2 * r]);
+    sm += stats_all[2 * r + 1];
+  }
+  const float gn = inv_rows / m;
+  *loss = sm * gn;
+  *g_norm = gn;
+}
+int sharded_loss_finalize(const float* stats_all, int world, long long rows, float* loss, float* g_norm, cudaStream_t stream) {
+  TT_CHECK(stats_all && loss && g_norm && world >= 1 && rows > 0, "sharded_loss_finalize: bad arguments");
+  KernelSpan span("sharded_loss_finalize_kernel", stream);
+  sharded_loss_finalize_kernel<<<1, 1, 0, stream>>>(stats_all, world, 1.f / (float)rows, loss, g_norm);
+  TT_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 
 static int pick_dp(long long d) { return d <= 64 ? 64 : (d <= 128 ? 128 : 256); }
 
@@ -568,13 +594,13 @@ int inbatch_ce_fwd_parts(const void* U, long long ldu, const void* const* Vp, in
                          long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
                          float* lse, void* ws, size_t ws_bytes, cudaStream_t stream) {
   return inbatch_ce_loss_fwd(U, ldu, Vp, np, rows_per_part, ldv, B, N, d, target_offset, ce, lse, nullptr, 0, nullptr, 0,
-                             nullptr, nullptr, nullptr, ws, ws_bytes, stream);
+                             nullptr, nullptr, nullptr, ws, ws_bytes, stream, nullptr);
 }
 
 int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
                         long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
                         float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
-                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream, float* stats) {
   const void* V = Vp[0];
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_fwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_fwd: embedding dim %lld > 256 is not supported", d);
@@ -616,7 +642,7 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
     KernelSpan span("ce_combine_loss_kernel", stream);
     ce_combine_loss_kernel<<<(unsigned)loss_blocks, 256, 0, stream>>>((int)B, Bpad, s.T, s.CT, a.part_m, a.part_s, dgo, ce,
                                                                       lse, labels, ldl, uvw, (int)TL, 1.f / (float)B, loss, g,
-                                                                      g_norm, a.sync);
+                                                                      g_norm, a.sync, stats);
     TT_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -627,6 +653,7 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
     TT_CUDA(cudaGetLastError());
     count_launch();
   }
+  TT_CHECK(stats == nullptr, "inbatch_ce_loss_fwd: the per-rank statistics need B <= %d rows per rank", LOSS_MAX_BLOCKS * COMBINE_RB);
   if (labels != nullptr) {  // very large batch: separate weighted-mean launch; g is already normalised
     set_scalar_kernel<<<1, 1, 0, stream>>>(g_norm, 1.f);
     TT_CUDA(cudaGetLastError());

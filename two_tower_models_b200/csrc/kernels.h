@@ -49,7 +49,9 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
 int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int np, long long rows_per_part,
                         long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
                         float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
-                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream);
+                        float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream, float* stats = nullptr);
+// stats (optional, [2]): this rank's (max nuv, sum ce nuv) for the batch-sharded loss; merged by sharded_loss_finalize
+int sharded_loss_finalize(const float* stats_all, int world, long long rows, float* loss, float* g_norm, cudaStream_t stream);
 // dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].
 int inbatch_ce_bwd(const void* U, long long ldu, const void* V, long long ldv, long long B, long long N, long long d,
                    long long target_offset, const float* lse, const float* g, float* dU, long long lddu, void* dU16,

@@ -11,6 +11,11 @@ north_star defines: one process per GPU (torchrun), every rank owns B_loc rows o
               --reduce-scatter(SUM)--> dV_loc;  dense parameter gradients --all-reduce(SUM)-- (the 1/N factor
               is already inside dL/dce, so gradients are summed, not averaged).
 
+Collectives per step (6, of which the id all-gather and the reduce-scatter run beside compute): all-gather(V) ->
+all-gather of the per-rank (max, sum) loss statistics -> reduce-scatter(dV), started after the dV pass and hidden
+behind the dU pass -> one all-gather of the touched embedding rows' gradients of BOTH towers (their ids were gathered
+on a side stream during the forward) -> one flat all-reduce of the dense parameter gradients.
+
 With these collectives a world_size-W run reproduces the single-process reference on the concatenated batch
 (same loss, same gradients up to fp reduction order) - tests/test_distributed_cpu.py checks that with gloo.
 
@@ -44,6 +49,21 @@ class _CudaKernels:
         ops.attach_shadow(dU, dU16)
         return dU, dV
 
+    # the two passes as separate launches, so that the reduce-scatter of dV overlaps the dU pass
+    @staticmethod
+    def ce_backward_dv(U_op, V_op, B, N, d, offset, lse, g, g_scale=None, g_scale2=None):
+        _, dV, _, dV16 = ops.inbatch_ce_backward_raw(U_op, V_op, B, N, d, offset, lse, g, g_scale=g_scale,
+                                                    g_scale2=g_scale2, want=("dV",))
+        return dV, dV16
+
+    @staticmethod
+    def ce_backward_du(U_op, V_op, B, N, d, offset, lse, g, g_scale=None, g_scale2=None):
+        cs = torch.zeros((2, d), dtype=torch.float32, device=U_op.device) if d <= 128 else None
+        dU, _, dU16, _ = ops.inbatch_ce_backward_raw(U_op, V_op, B, N, d, offset, lse, g, g_scale=g_scale,
+                                                    g_scale2=g_scale2, want=("dU",), colsums=cs)
+        ops.attach_shadow(dU, dU16, None if cs is None else cs[0])
+        return dU
+
 
 def _reduce_scatter_sum(full: torch.Tensor, rank: int, world: int, group) -> torch.Tensor:
     rows = full.shape[0] // world
@@ -53,6 +73,32 @@ def _reduce_scatter_sum(full: torch.Tensor, rank: int, world: int, group) -> tor
     out = torch.empty((rows,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
     dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+_RS_BF16 = __import__("os").environ.get("TT_B200_RS_BF16", "1") == "1"
+
+
+def _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d):
+    """Start the reduce-scatter of the items' gradient (async on NCCL's stream) and return a closure that waits for it
+    and returns the local fp32 dV [B, d] (bf16 operand copy attached).  By default the bf16 copy travels (half the
+    bytes; the tower backward consumes dV as a bf16 operand anyway) - TT_B200_RS_BF16=0 sends fp32."""
+    rows = dV_all.shape[0] // world
+    if dV_all16 is not None and _RS_BF16:
+        out16 = torch.empty((rows, dV_all16.shape[1]), dtype=dV_all16.dtype, device=dV_all16.device)
+        work = dist.reduce_scatter_tensor(out16, dV_all16, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+        def finish():
+            work.wait()
+            dV = out16[:, :d].float()
+            return ops.attach_shadow(dV, out16)
+    else:
+        out = torch.empty((rows, d), dtype=dV_all.dtype, device=dV_all.device)
+        work = dist.reduce_scatter_tensor(out, dV_all.contiguous(), op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+        def finish():
+            work.wait()
+            return out
+    return finish
 
 
 class ShardedInBatchCE(torch.autograd.Function):
@@ -76,9 +122,66 @@ class ShardedInBatchCE(torch.autograd.Function):
     def backward(ctx, g):
         U_op, V_all, lse = ctx.saved_tensors
         B, d, rank, world, group, kernels = ctx.meta
-        dU, dV_all = kernels.ce_backward(U_op, V_all, B, world * B, d, rank * B, lse, g.contiguous().float())
+        g = g.contiguous().float()
+        if hasattr(kernels, "ce_backward_dv") and dist.get_backend(group) != "gloo":
+            dV_all, dV_all16 = kernels.ce_backward_dv(U_op, V_all, B, world * B, d, rank * B, lse, g)
+            finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d)  # runs beside the dU pass
+            dU = kernels.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g)
+            return dU, finish(), None, None
+        dU, dV_all = kernels.ce_backward(U_op, V_all, B, world * B, d, rank * B, lse, g)
         dV = _reduce_scatter_sum(dV_all, rank, world, group)
         return dU, dV, None, None
+
+
+class ShardedWeightedLoss(torch.autograd.Function):
+    """compute_training_loss with the identity hook, batch-sharded, CUDA kernels only: all-gather(V), ONE fused launch for
+    scores + softmax statistics + label weights + this rank's (max nuv, sum ce nuv), one all-gather of those pairs and
+    a one-thread kernel that folds them into the global loss and the scalar the backward kernels multiply into g."""
+
+    @staticmethod
+    def forward(ctx, U, V, labels, weights, group):
+        from . import _native
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        B, d = U.shape
+        if V.shape != (B, d):
+            raise RuntimeError(f"user/item embeddings must both be [{B}, {d}] on every rank, got {tuple(V.shape)}")
+        U_op, V_op = _CudaKernels.operand(U), _CudaKernels.operand(V)
+        dev = U_op.device
+        N = world * B
+        V_all = torch.empty((N,) + tuple(V_op.shape[1:]), dtype=V_op.dtype, device=dev)
+        dist.all_gather_into_tensor(V_all, V_op.contiguous(), group=group)
+        labels, weights = ops._f32c(labels), ops._f32c(weights)
+        out = torch.empty(3 * B + 1, dtype=torch.float32, device=dev)  # ce | lse | g | g_norm (saved for backward)
+        ce, lse, g, g_norm = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:]
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        ws = ops._ce_workspace(B, N, d, dev)
+        L = _native.lib()
+        _native.check(
+            L.tt_inbatch_ce_loss_fwd_sharded(U_op.data_ptr(), U_op.stride(0), V_all.data_ptr(), V_all.stride(0), B, N, d,
+                                             rank * B, labels.data_ptr(), labels.stride(0), weights.data_ptr(),
+                                             labels.shape[1], ce.data_ptr(), lse.data_ptr(), g.data_ptr(), stats.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), ops._stream()),
+            "inbatch_ce_loss_fwd_sharded")
+        stats_all = torch.empty(2 * world, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(stats_all, stats[:2], group=group)
+        _native.check(L.tt_sharded_loss_finalize(stats_all.data_ptr(), world, N, loss.data_ptr(), g_norm.data_ptr(),
+                                                 ops._stream()), "sharded_loss_finalize")
+        ctx.save_for_backward(U_op, V_all, lse, g, g_norm)
+        ctx.meta = (B, d, rank, world, group)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        U_op, V_all, lse, g, g_norm = ctx.saved_tensors
+        B, d, rank, world, group = ctx.meta
+        gs = ops._f32c(dloss).reshape(1)
+        K = _CudaKernels
+        dV_all, dV_all16 = K.ce_backward_dv(U_op, V_all, B, world * B, d, rank * B, lse, g, g_scale=gs, g_scale2=g_norm)
+        finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d)  # runs beside the dU pass
+        dU = K.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g, g_scale=gs, g_scale2=g_norm)
+        return dU, finish(), None, None, None
 
 
 class _PeerItemBuffers:
@@ -134,6 +237,72 @@ class PeerShardedInBatchCE(torch.autograd.Function):
         return dU, dV, None, None
 
 
+class _RowExchange:
+    """Sparse exchange of the id-embedding gradients: every rank contributes its touched (id, row gradient) pairs instead
+    of all-reducing dense [hash, D] tables.  One object serves all towers of a step:
+      start_ids(ids of all towers, concatenated)  - forward: all-gather on a side stream, long before it is needed;
+      gather_rows(row gradients of all towers)     - backward: ONE all-gather for every tower;
+      ids_for(handle, t)                           - tower t's ids in the gathered order, the other towers' slots masked
+                                                     to -1 (the scatter-add kernel skips them without touching the row).
+    Called as a function (ids, rows) it exchanges one tower on its own (ops.TowerFunction)."""
+
+    def __init__(self, group, world):
+        self.group, self.world = group, world
+        self._masks = {}
+
+    def __call__(self, ids, rows):
+        world, group = self.world, self.group
+        ids_all = torch.empty((world * ids.shape[0],), dtype=ids.dtype, device=ids.device)
+        rows_all = torch.empty((world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=group)
+        dist.all_gather_into_tensor(rows_all, rows, group=group)
+        return ids_all, rows_all
+
+    def _mask(self, towers, rows, t, device):
+        key = (towers, rows, t, str(device))
+        m = self._masks.get(key)
+        if m is None:
+            slot = torch.arange(towers * rows, device=device).div(rows, rounding_mode="floor").repeat(self.world)
+            m = slot != t
+            self._masks[key] = m
+        return m
+
+    def start_ids(self, ids_cat, towers):
+        """ids_cat: int64 [towers * rows].  Returns a handle for ids_for()."""
+        dev = ids_cat.device
+        rows = ids_cat.shape[0] // towers
+        masks = [self._mask(towers, rows, t, dev) for t in range(towers)]  # (built outside the side stream once)
+        side = None
+        if ids_cat.is_cuda:
+            cur = torch.cuda.current_stream(dev)
+            side = ops._aux_stream(dev, 3)
+            side.wait_stream(cur)
+        ctxm = torch.cuda.stream(side) if side is not None else __import__("contextlib").nullcontext()
+        with ctxm:
+            ids_all = torch.empty((self.world * ids_cat.shape[0],), dtype=ids_cat.dtype, device=dev)
+            dist.all_gather_into_tensor(ids_all, ids_cat, group=self.group)
+            per_tower = [ids_all.masked_fill(m, -1) for m in masks]
+            ev = None
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+        if side is not None:
+            ids_cat.record_stream(side)
+        return per_tower, ev
+
+    def ids_for(self, handle, t):
+        per_tower, ev = handle
+        if ev is not None:
+            torch.cuda.current_stream(per_tower[t].device).wait_event(ev)
+            per_tower[t].record_stream(torch.cuda.current_stream(per_tower[t].device))
+        return per_tower[t]
+
+    def gather_rows(self, rows_cat):
+        rows_all = torch.empty((self.world * rows_cat.shape[0], rows_cat.shape[1]), dtype=rows_cat.dtype, device=rows_cat.device)
+        dist.all_gather_into_tensor(rows_all, rows_cat.contiguous(), group=self.group)
+        return rows_all
+
+
 class DataParallelContext:
     def __init__(self, group=None, kernels=None, peer_memory=None):
         if not dist.is_initialized():
@@ -149,6 +318,7 @@ class DataParallelContext:
             peer_memory = os.environ.get("TT_B200_PEER_CE", "0") == "1"
         self.peer_memory = bool(peer_memory) and kernels is None
         self._peers = None
+        self._row_exchange = None
 
     def compute_training_loss(self, model, user_embedding, item_embeddings, position, labels):
         """Sharded version of TwoTowerBaseRetrieval.compute_training_loss (reference :279-347); the
@@ -160,24 +330,36 @@ class DataParallelContext:
                 self._peers = _PeerItemBuffers(self.group, B, pitch, item_embeddings.device)
             ce = PeerShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self._peers)  # [B_loc]
         else:
+            from .towers import TwoTowerBaseRetrieval
+
+            if (self.kernels is _CudaKernels and user_embedding.is_cuda
+                    and getattr(type(model), "debias_net_user_value", None) is TwoTowerBaseRetrieval.debias_net_user_value
+                    and labels.dim() == 2 and labels.shape[1] == model.user_value_weights.shape[0]
+                    and not labels.requires_grad and user_embedding.shape[0] <= 65536):
+                # identity hook: weights, batch max and the weighted mean ride in the CE's merge kernel on every rank
+                return ShardedWeightedLoss.apply(user_embedding, item_embeddings, labels, model.user_value_weights, self.group)
             ce = ShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self.kernels)  # [B_loc]
         net_user_value = torch.sum(labels * model.user_value_weights, dim=-1)
         net_user_value, additional_loss = model.debias_net_user_value(
             net_user_value=net_user_value, position=position, user_embedding=user_embedding
         )
         net_user_value = torch.clamp(net_user_value, min=0.000001)
-        gmax = torch.max(net_user_value).detach().clone()
-        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)  # batch-global max (reference :339)
-        net_user_value = net_user_value / gmax
-        n_global = ce.shape[0] * self.world
-        local = torch.sum(ce * net_user_value) / n_global  # this rank's share of mean over the global batch
-        total = local.detach().clone()
-        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
-        # value = global loss, gradient = this rank's share (gradients are summed across ranks afterwards)
-        loss = local + (total - local.detach())
-        if torch.is_tensor(additional_loss):
-            return loss + additional_loss / self.world
-        return loss + additional_loss
+        # ONE small all-gather carries every rank's (max weight, sum ce * weight, additional loss): the batch-global max
+        # (reference :339), the global mean (:343) and the global sum of the hook's additional loss (:346)
+        has_aux = torch.is_tensor(additional_loss)
+        s_loc = torch.sum(ce * net_user_value)
+        vec = torch.stack([torch.max(net_user_value).detach().reshape(()).float(), s_loc.detach().float(),
+                           (additional_loss.detach().reshape(()).float() if has_aux
+                            else torch.zeros((), dtype=torch.float32, device=ce.device))])
+        gathered = torch.empty(3 * self.world, dtype=torch.float32, device=ce.device)
+        dist.all_gather_into_tensor(gathered, vec, group=self.group)
+        gathered = gathered.view(self.world, 3)
+        scale = 1.0 / (gathered[:, 0].max() * (ce.shape[0] * self.world))
+        # gradient = this rank's share (gradients are summed across ranks afterwards; the additional loss is a sum over
+        # the batch in the reference, so its local part enters unscaled); value = the global loss
+        local = s_loc * scale + (additional_loss if has_aux else 0.0)
+        value = gathered[:, 1].sum() * scale + (gathered[:, 2].sum() if has_aux else additional_loss)
+        return local + (value - local.detach())
 
     def row_exchange(self, model, table):
         """Sparse exchange of an id-embedding table's gradient: every rank contributes its B_loc touched
@@ -188,16 +370,9 @@ class DataParallelContext:
         if getattr(model, "user_history_encoder", None) is not None and table is model.item_id_embedding_arch.weight:
             return None
         self._presynced.add(id(table))
-        group, world = self.group, self.world
-
-        def exchange(ids, rows):
-            ids_all = torch.empty((world * ids.shape[0],), dtype=ids.dtype, device=ids.device)
-            rows_all = torch.empty((world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
-            dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=group)
-            dist.all_gather_into_tensor(rows_all, rows, group=group)
-            return ids_all, rows_all
-
-        return exchange
+        if self._row_exchange is None:
+            self._row_exchange = _RowExchange(self.group, self.world)
+        return self._row_exchange
 
     def sync_gradients(self, model) -> None:
         """Sum parameter gradients over the ranks (call after loss.backward()).  Dense parameters travel in

@@ -26,10 +26,22 @@ class GraphedTrainStep:
         self.model = model
         self.post_backward = post_backward  # e.g. DataParallelContext.sync_gradients
         self.optimizer = optimizer  # e.g. FusedAdam: its step is captured after the backward (device-side step counter)
-        self.static = {k: example_batch[k].clone() for k in ORDER}
-        dev = self.static["user_id"].device
+        dev = example_batch["user_id"].device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (two_tower_models_b200 has no CPU path)")
+        # the captured inputs are views of ONE flat buffer: a batch that was packed the same way (pack() / new_slot())
+        # is loaded with a single copy instead of seven
+        self._layout, off = [], 0
+        for k in ORDER:
+            t = example_batch[k]
+            n = t.numel() * t.element_size()
+            self._layout.append((k, off, n, t.dtype, tuple(t.shape)))
+            off += (n + 255) // 256 * 256
+        self._flat_bytes = off
+        self._flat = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.static = self._views(self._flat)
+        for k in ORDER:
+            self.static[k].copy_(example_batch[k])
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -62,8 +74,28 @@ class GraphedTrainStep:
             self.optimizer.step()
         return loss.detach()
 
+    def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {k: flat[o:o + n].view(dt).view(shape) for (k, o, n, dt, shape) in self._layout}
+
+    def new_slot(self, batch: Dict[str, torch.Tensor] = None, device=None, pin_memory: bool = False) -> Dict[str, torch.Tensor]:
+        """A batch-shaped set of tensors backed by one flat buffer with the layout of the captured inputs (on `device`,
+        default the model's; pin_memory=True for a host staging slot), optionally filled from `batch`.  load() moves
+        such a slot with ONE copy."""
+        device = self._flat.device if device is None else torch.device(device)
+        flat = torch.empty(self._flat_bytes, dtype=torch.uint8, device=device, pin_memory=pin_memory and device.type == "cpu")
+        slot = self._views(flat)
+        slot["_flat"] = flat
+        if batch is not None:
+            for k in ORDER:
+                slot[k].copy_(batch[k])
+        return slot
+
     def load(self, batch: Dict[str, torch.Tensor], non_blocking: bool = True) -> None:
         """Copy a batch (device or pinned host tensors) into the static input buffers."""
+        flat = batch.get("_flat")
+        if flat is not None and flat.numel() == self._flat_bytes:
+            self._flat.copy_(flat, non_blocking=non_blocking)
+            return
         for k in ORDER:
             self.static[k].copy_(batch[k], non_blocking=non_blocking)
 

@@ -519,23 +519,27 @@ def inbatch_ce_forward_raw(U16, V16, B, N, d, target_offset=0):
     return ce, lse
 
 
-def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True, colsums=None, g_scale=None, g_scale2=None):
+def inbatch_ce_backward_raw(U16, V16, B, N, d, target_offset, lse, g, want_bf16=True, colsums=None, g_scale=None,
+                            g_scale2=None, want=("dU", "dV")):
     """colsums: optional zero-initialised fp32 [2, d] receiving the column sums of dU and dV (d <= 128).
-    g_scale, g_scale2: optional one-element fp32 device tensors multiplied into g inside the kernels."""
+    g_scale, g_scale2: optional one-element fp32 device tensors multiplied into g inside the kernels.
+    want: which gradients to compute (each is one pass over the score tiles); the others come back as None."""
     dev = U16.device
-    dU = torch.empty((B, d), dtype=torch.float32, device=dev)
-    dV = torch.empty((N, d), dtype=torch.float32, device=dev)
-    dU16 = torch.empty((B, _r8(d)), dtype=_BF16, device=dev) if want_bf16 else None
-    dV16 = torch.empty((N, _r8(d)), dtype=_BF16, device=dev) if want_bf16 else None
+    wu, wv = "dU" in want, "dV" in want
+    dU = torch.empty((B, d), dtype=torch.float32, device=dev) if wu else None
+    dV = torch.empty((N, d), dtype=torch.float32, device=dev) if wv else None
+    dU16 = torch.empty((B, _r8(d)), dtype=_BF16, device=dev) if (want_bf16 and wu) else None
+    dV16 = torch.empty((N, _r8(d)), dtype=_BF16, device=dev) if (want_bf16 and wv) else None
     ws = _ce_workspace(B, N, d, dev)
     with _span("inbatch_ce_bwd"):
         _native.check(
             _native.lib().tt_inbatch_ce_bwd_scaled(
                 U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d, target_offset,
-                lse.data_ptr(), g.data_ptr(), _ptr(g_scale), _ptr(g_scale2), dU.data_ptr(), dU.stride(0), _ptr(dU16),
-                dU16.stride(0) if want_bf16 else 0, dV.data_ptr(), dV.stride(0), _ptr(dV16),
-                dV16.stride(0) if want_bf16 else 0,
-                None if colsums is None else colsums.data_ptr(), None if colsums is None else colsums.data_ptr() + 4 * d,
+                lse.data_ptr(), g.data_ptr(), _ptr(g_scale), _ptr(g_scale2), _ptr(dU), d if wu else 0, _ptr(dU16),
+                dU16.stride(0) if dU16 is not None else 0, _ptr(dV), d if wv else 0, _ptr(dV16),
+                dV16.stride(0) if dV16 is not None else 0,
+                None if (colsums is None or not wu) else colsums.data_ptr(),
+                None if (colsums is None or not wv) else colsums.data_ptr() + 4 * d,
                 ws.data_ptr(), ws.numel(), _stream()),
             "inbatch_ce_bwd",
         )
@@ -1030,6 +1034,13 @@ class TowerSetFunction(torch.autograd.Function):
             late_fill = _LATE_ZERO_FILL and all(spec[1] is None for spec in specs)
             if zero_jobs and not late_fill:
                 cur, ev = start_fills()
+            # data parallel, every tower exchanging row-wise through the same object: the ids of ALL towers travel in
+            # one all-gather on a side stream now; the backward then needs a single all-gather of row gradients
+            xch = specs[0][1]
+            ctx.ids_handle = None
+            if (xch is not None and hasattr(xch, "start_ids") and all(sp[1] is xch for sp in specs)
+                    and len({(d["B"], d["D8"], d["D"]) for d in tw}) == 1):
+                ctx.ids_handle = xch.start_ids(torch.cat([d["ids"] for d in tw]), T)
             if casts:
                 cast_batched(casts)
             fused = [d for d in tw if d["fused"]]
@@ -1137,7 +1148,15 @@ class TowerSetFunction(torch.autograd.Function):
                 gemm_batched([dict(A=d["dX16"][:, d["D8"]:], B=d["H16"], M=d["D"], N=d["hid"], K=d["B"], a_mn=True, b_mn=True,
                                    out32=d["dW1"], accumulate=True) for d in tw])
             with torch.cuda.stream(s2):  # id embeddings (dense gradient, duplicates accumulate)
+                if ctx.ids_handle is not None:  # one all-gather of the row gradients of every tower
+                    xch = tw[0]["row_exchange"]
+                    rows_all = xch.gather_rows(torch.cat([d["dX16"][:, :d["D8"]] for d in tw]))
+                    for t, d in enumerate(tw):
+                        d["dtable_out"] = scatter_add_rows(rows_all, xch.ids_for(ctx.ids_handle, t), d["D"], d["table_rows"],
+                                                           col_offset=0, grad=d.pop("dtable_buf"))
                 for d in tw:
+                    if "dtable_out" in d:
+                        continue
                     pre = d.pop("dtable_buf")
                     if d["row_exchange"] is not None:
                         ids_all, rows_all = d["row_exchange"](d["ids"], d["dX16"][:, :d["D8"]].contiguous())
