@@ -1,22 +1,34 @@
 #!/bin/bash
-# round-end evidence on one B200: parity tests, smoke, the three bench workloads, the reference arm, ncu launch list and
-# full captures of the dominant kernels.  Everything lands in gpurun_out/ (copy what should be judged into profiles/).
+# round-end evidence on one B200 (everything lands in gpurun_out/r02_*; copy what should be judged into profiles/):
+# parity tests, smoke, the driver's bench line + reference arm, step breakdown / timeline, ncu launch list, ncu --set full of
+# the step's kernels and of the history / MIPS kernels, compute-sanitizer over the CE parity tests, CE backward timelines.
 mkdir -p gpurun_out
+O=gpurun_out
+C=$PWD/two_tower_models_b200/csrc
 bash tools/gpu_tests.sh 2>&1 | grep -E "rc=|passed|failed"
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-timeout 900 python bench.py --workload history --steps 20 --warmup 5 > gpurun_out/bench_history.json 2> gpurun_out/bench_history.err; echo "history rc=$?"
-timeout 900 python bench.py --workload mips --steps 2 --warmup 1 > gpurun_out/bench_mips.json 2> gpurun_out/bench_mips.err; echo "mips rc=$?"
-python tools/step_breakdown.py 2>&1 | grep -v -i "warn\|return Variable" | tail -6 > gpurun_out/step_breakdown.txt; cat gpurun_out/step_breakdown.txt
-python tools/step_timeline.py 2>&1 | grep -v -i "warn\|return Variable" | tail -24 | cut -c1-110 > gpurun_out/step_timeline.txt
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ce_fwd_kernel|ce_bwd2_kernel|tower_fwd_kernel|adam_kernel|ce_bwd_reduce|ce_combine_loss" -s 12 -c 8 -f -o gpurun_out/prof_step_final python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv 2>&1 | tail -4
-python -c "
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee $O/r02_smoke.txt
+timeout 900 python bench.py --steps 20 --warmup 5 > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_reference_arm.json 2> $O/r02_bench_ref.err; echo "ref rc=$?"
+python tools/step_breakdown.py 2>&1 | grep -v -i "warn\|return Variable" | tail -6 > $O/r02_step_breakdown.txt; cat $O/r02_step_breakdown.txt
+python tools/step_timeline.py 2>&1 | grep -v -i "warn\|return Variable" | tail -26 | cut -c1-120 > $O/r02_step_timeline.txt
+timeout 300 python tools/ce_time.py 64 128 256 > $O/r02_ce_time.txt 2>&1; cat $O/r02_ce_time.txt
+TT_B200_LIB=$C/libtt_b200_bringup.so timeout 300 python tools/trace_ce.py 128 > $O/r02_ce_bwd3_timeline_dU.txt 2>&1
+TT_B200_LIB=$C/libtt_b200_bringup.so timeout 300 python tools/trace_ce.py 128 dv > $O/r02_ce_bwd3_timeline_dV.txt 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_step_launches_ncu.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --no-extra-legs > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ce_fwd_kernel|ce_bwd3_kernel|tower_fwd_kernel|ce_bwd_reduce|ce_combine_loss|gemm_kernel" -s 14 -c 12 -f -o $O/prof_step_r02 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-extra-legs > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attn_fwd_tc_kernel|attn_bwd_tc_kernel|gemm_kernel" -s 30 -c 10 -f -o $O/prof_history_r02 python bench.py --workload history --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mips_screen_kernel|mips_finalize" -s 2 -c 2 -f -o $O/prof_mips_r02 python bench.py --workload mips --steps 1 --warmup 1 --no-cpu-baseline --queries 16384 > /dev/null 2>&1
+ls -la $O/*.ncu-rep 2>&1 | tail -4
+# compute-sanitizer over the CE parity tests (hand-rolled mbarrier / TMEM protocols): memcheck, then synccheck
+for tool in memcheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -x -k "inbatch_ce and (128-128-64 or 300-300-128 or 256-1024-128 or 200-456-256)" > $O/r02_sanitizer_$tool.txt 2>&1
+  echo "sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Error" $O/r02_sanitizer_$tool.txt | tail -4
+done
+python - <<'PY'
 import json
-for f in ['bench_n1','bench_history','bench_mips','bench_ref']:
+for f in ['r02_bench_n1','r02_bench_reference_arm']:
     try:
-        d=json.load(open('gpurun_out/%s.json'%f)); print(f, round(d['value']), d['unit'], 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']))
+        d=json.load(open('gpurun_out/%s.json'%f)); print(f, round(d['value']), d['unit'], 'ms/step', round(d['ms_per_step'],4), 'e2e', d['e2e'] and round(d['e2e']['value']))
+        for k,v in d.get('configs',{}).items(): print('  ', k, v.get('error') or (round(v['value']), v['unit'], round(v['ms_per_step'],4), v.get('roofline') and round(v['roofline']['frac'],3)))
     except Exception as e: print(f, 'ERR', e)
-"
+PY
