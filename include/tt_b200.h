@@ -288,6 +288,24 @@ int tt_inbatch_ce_bwd_parts(const void* U_bf16, int64_t ldu, const void* const* 
                             float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
                             float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- last history-encoder layer, query row 0 only ------------------------------------------ */
+
+/* The reference consumes row 0 of the last nn.MultiheadAttention layer only (src/user_history_encoder.py:116).  For a
+ * single query row the keys / values need not be projected: with qt_h = c Wk_h^T q0_h (c = head_dim^-1/2) the scores are
+ * qt_h . x_j against the RAW layer input x and the head output is Wv_h (sum_j p_j x_j) + bv_h.  These three entry points
+ * are the memory-bound part (one warp per sequence); the [B, .]-sized projections around them are tt_gemm_bf16 calls.
+ *   fwd : p[b,h,:] = softmax_j(qt[b,h,:] . x[b*H+j,:]);  z[b,h,:] = sum_j p[b,h,j] x[b*H+j,:]   (z bf16 [B, heads*D])
+ *   bwd1: ds = p (dz . x - sum p (dz . x));  dqt[b,h,:] = sum_j ds[b,h,j] x[b*H+j,:]               (dqt bf16)
+ *   bwd2: dx[b*H+j,:] = sum_h (p[b,h,j] dz[b,h,:] + ds[b,h,j] qt[b,h,:]) (+ extra[b,:] on row j = 0); colsum += sum rows
+ * D in {64, 128}, H <= 128, heads <= 8, head_dim % 8 == 0 (tt_history_last_supported). */
+int tt_history_last_supported(int64_t H, int64_t D, int64_t heads);
+int tt_history_last_fwd(const void* x_bf16, int64_t ldx, const float* qt, int64_t B, int64_t H, int64_t D, int64_t heads,
+                        void* z_bf16, float* p, void* stream);
+int tt_history_last_bwd1(const void* x_bf16, int64_t ldx, const float* dz, const float* p, int64_t B, int64_t H, int64_t D,
+                         int64_t heads, float* ds, void* dqt_bf16, void* stream);
+int tt_history_last_bwd2(const float* dz, const float* qt, const float* p, const float* ds, const float* extra, int64_t B,
+                         int64_t H, int64_t D, int64_t heads, void* dx_bf16, int64_t lddx, float* colsum, void* stream);
+
 /* ---- history encoder helpers ---------------------------------------------------------------- */
 
 /* x_bf16[b*H+h, :] = bf16(table[ids[b,h]] + pe[h]) (pe may be NULL);  mean[b, :] = mean_h table[ids[b,h]].

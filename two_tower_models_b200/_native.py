@@ -111,6 +111,10 @@ SIGNATURES = {
     "tt_weighted_loss": (I32, [P, P, I64, P, I64, I64, P, P, P]),
     "tt_inbatch_ce_loss_fwd_sharded": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, I64, P, I64, P, P, P, P, P, I64, P]),
     "tt_sharded_loss_finalize": (I32, [P, I32, I64, P, P, P]),
+    "tt_history_last_supported": (I32, [I64, I64, I64]),
+    "tt_history_last_fwd": (I32, [P, I64, P, I64, I64, I64, I64, P, P, P]),
+    "tt_history_last_bwd1": (I32, [P, I64, P, P, I64, I64, I64, I64, P, P, P]),
+    "tt_history_last_bwd2": (I32, [P, P, P, P, P, I64, I64, I64, I64, P, I64, P, P]),
     "tt_mips_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "tt_mips_topk": (I32, [P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I64, P, P, P, I64, P]),
     "tt_history_gather_pool": (I32, [P, I64, I64, P, I64, I64, P, P, I64, P, I64, P, P]),

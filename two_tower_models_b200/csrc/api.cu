@@ -276,6 +276,22 @@ int tt_inbatch_ce_loss_fwd(const void* U, int64_t ldu, const void* V, int64_t ld
   return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, loss, g, g_norm,
                              ws, (size_t)ws_bytes, S(stream));
 }
+int tt_history_last_supported(int64_t H, int64_t D, int64_t heads) { return history_last_supported(H, D, heads); }
+int tt_history_last_fwd(const void* x16, int64_t ldx, const float* qt, int64_t B, int64_t H, int64_t D, int64_t heads, void* z16,
+                        float* p32, void* stream) {
+  TT_CHECK(x16 && qt && z16 && p32, "tt_history_last_fwd: null argument");
+  return history_last_fwd(x16, ldx, qt, B, H, D, heads, z16, p32, S(stream));
+}
+int tt_history_last_bwd1(const void* x16, int64_t ldx, const float* dz, const float* p32, int64_t B, int64_t H, int64_t D,
+                         int64_t heads, float* ds32, void* dqt16, void* stream) {
+  TT_CHECK(x16 && dz && p32 && ds32 && dqt16, "tt_history_last_bwd1: null argument");
+  return history_last_bwd1(x16, ldx, dz, p32, B, H, D, heads, ds32, dqt16, S(stream));
+}
+int tt_history_last_bwd2(const float* dz, const float* qt, const float* p32, const float* ds32, const float* extra, int64_t B,
+                         int64_t H, int64_t D, int64_t heads, void* dx16, int64_t lddx, float* colsum, void* stream) {
+  TT_CHECK(dz && qt && p32 && ds32 && dx16, "tt_history_last_bwd2: null argument");
+  return history_last_bwd2(dz, qt, p32, ds32, extra, B, H, D, heads, dx16, lddx, colsum, S(stream));
+}
 int tt_inbatch_ce_loss_fwd_sharded(const void* U, int64_t ldu, const void* V, int64_t ldv, int64_t B, int64_t N, int64_t d,
                                    int64_t target_offset, const float* labels, int64_t ldl, const float* weights, int64_t T,
                                    float* ce, float* lse, float* g, float* stats, void* ws, int64_t ws_bytes, void* stream) {

@@ -168,6 +168,15 @@ int tower_bwd_chain(const TowerBwdProblem* problems, int n, cudaStream_t stream)
 bool tower_fwd_supported(long long F, long long D, long long DI, long long hidden);
 int tower_fwd(const TowerProblem* problems, int n, int* oob_flag, cudaStream_t stream);
 
+// Last history-encoder layer evaluated for query row 0 only, against the raw layer input (csrc/history_last.cu)
+int history_last_supported(long long H, long long D, long long heads);
+int history_last_fwd(const void* x16, long long ldx, const float* qt, long long B, long long H, long long D, long long heads,
+                     void* z16, float* p32, cudaStream_t stream);
+int history_last_bwd1(const void* x16, long long ldx, const float* dz, const float* p32, long long B, long long H, long long D,
+                      long long heads, float* ds32, void* dqt16, cudaStream_t stream);
+int history_last_bwd2(const float* dz, const float* qt, const float* p32, const float* ds32, const float* extra, long long B,
+                      long long H, long long D, long long heads, void* dx16, long long lddx, float* colsum, cudaStream_t stream);
+
 // Fused multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off); *step is a device counter bumped by the launch.
 struct AdamTensor {
   float* p;

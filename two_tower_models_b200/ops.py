@@ -757,12 +757,38 @@ class HistoryEncoderFunction(torch.autograd.Function):
         _maybe_check_ids(dev, "history lookup")
         saved = []
         recent = summary[:, :D]
+        hd = D // heads if heads else 0
+        # last layer: only query row 0 is consumed (reference :116) -> attention against the RAW layer input, no key / value
+        # projection of the H rows (csrc/history_last.cu); other shapes take the generic kernels with q_rows = 1
+        fast_last = (_HISTORY_LAST_FAST and L >= 1 and D8 == D and heads >= 1 and D % heads == 0
+                     and bool(lib.tt_history_last_supported(H, D, heads)))
         for l in range(L):
             in_w, in_b, out_w, out_b = params[4 * l: 4 * l + 4]
             last = l == L - 1
             q_rows = 1 if last else H
             in_w16 = packed.get(f"{tag}.{l}.in", in_w)
             out_w16 = packed.get(f"{tag}.{l}.out", out_w)
+            if last and fast_last:
+                in_b32 = _f32c(in_b)
+                c = float(hd) ** -0.5
+                x0 = x16.view(B, H, D8)[:, 0]  # [B, D] view, row pitch H * D8
+                q0_16 = torch.empty((B, D8), dtype=_BF16, device=dev)
+                gemm(x0, in_w16[:D], B, D, D, bias=in_b32[:D], out16=q0_16)
+                qt32 = torch.empty((B, heads * D), dtype=torch.float32, device=dev)
+                gemm_batched([dict(A=q0_16[:, h * hd:(h + 1) * hd], B=in_w16[D + h * hd:D + (h + 1) * hd], M=B, N=D, K=hd,
+                                   b_mn=True, alpha=c, out32=qt32[:, h * D:(h + 1) * D]) for h in range(heads)])
+                z16 = torch.empty((B, heads * D), dtype=_BF16, device=dev)
+                p32 = torch.empty((B, heads, H), dtype=torch.float32, device=dev)
+                with _span("hist_last_fwd"):
+                    _native.check(lib.tt_history_last_fwd(x16.data_ptr(), x16.stride(0), qt32.data_ptr(), B, H, D, heads,
+                                                          z16.data_ptr(), p32.data_ptr(), _stream()), "history_last_fwd")
+                o16 = torch.empty((B, D8), dtype=_BF16, device=dev)
+                gemm_batched([dict(A=z16[:, h * D:(h + 1) * D], B=in_w16[2 * D + h * hd:2 * D + (h + 1) * hd], M=B, N=hd, K=D,
+                                   bias=in_b32[2 * D + h * hd:2 * D + (h + 1) * hd], out16=o16[:, h * hd:(h + 1) * hd])
+                              for h in range(heads)])
+                gemm(o16, out_w16, B, D, D, bias=_f32c(out_b), out32=recent)
+                saved += [x16, q0_16, qt32, z16, p32, o16, in_w16, out_w16]
+                continue
             qkv16 = torch.empty((B * H, Q8), dtype=_BF16, device=dev)
             gemm(x16, in_w16, B * H, 3 * D, D, bias=_f32c(in_b), out16=qkv16)
             o16 = attn_forward(qkv16, B, H, D, heads, q_rows)
@@ -773,8 +799,11 @@ class HistoryEncoderFunction(torch.autograd.Function):
                 y16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
                 gemm(o16, out_w16, B * H, D, D, bias=_f32c(out_b), out16=y16)
                 x16 = y16
+        if L == 0:  # no attention layer: the "most recent" half is row 0 of the (position-encoded) input itself
+            recent.copy_(x16.view(B, H, D8)[:, 0, :D])
         ctx.save_for_backward(ids_, *saved)
         ctx.dims = (B, H, D, heads, L, table.shape[0], ids is None, tuple(src.shape))
+        ctx.fast_last = fast_last
         return summary
 
     @staticmethod
@@ -789,9 +818,52 @@ class HistoryEncoderFunction(torch.autograd.Function):
         dy_sum = colsum(ds[:, :D], D)      # its fp32 column sums (= last out-projection bias gradient)
         dmean = ds[:, D:]
         grads = [None] * (4 * L)
+        hd = D // heads if heads else 0
+        if L == 0:  # gradient of row 0 only
+            full = torch.zeros((B, H, D8), dtype=_BF16, device=dev)
+            full[:, 0] = dy16
+            dy16 = full.view(B * H, D8)
         for l in range(L - 1, -1, -1):
-            x16, qkv16, o16, in_w16, out_w16 = saved[5 * l: 5 * l + 5]
             last = l == L - 1
+            if last and ctx.fast_last:
+                x16, q0_16, qt32, z16, p32, o16, in_w16, out_w16 = saved[5 * l: 5 * l + 8]
+                c = float(hd) ** -0.5
+                d_out_w = torch.zeros((D, D), dtype=torch.float32, device=dev)
+                gemm(dy16, o16, D, D, B, a_mn=True, b_mn=True, out32=d_out_w, accumulate=True)
+                d_out_b = dy_sum
+                d_in_w = torch.zeros((3 * D, D), dtype=torch.float32, device=dev)
+                d_in_b = torch.zeros(3 * D, dtype=torch.float32, device=dev)
+                do16 = torch.empty((B, D8), dtype=_BF16, device=dev)
+                gemm(dy16, out_w16, B, D, D, b_mn=True, out16=do16, colsum=d_in_b[2 * D:])  # + column sums = d bv
+                dz32 = torch.empty((B, heads * D), dtype=torch.float32, device=dev)
+                gemm_batched([dict(A=do16[:, h * hd:(h + 1) * hd], B=in_w16[2 * D + h * hd:2 * D + (h + 1) * hd], M=B, N=D, K=hd,
+                                   b_mn=True, out32=dz32[:, h * D:(h + 1) * D]) for h in range(heads)])
+                gemm_batched([dict(A=do16[:, h * hd:(h + 1) * hd], B=z16[:, h * D:(h + 1) * D], M=hd, N=D, K=B, a_mn=True, b_mn=True,
+                                   out32=d_in_w[2 * D + h * hd:2 * D + (h + 1) * hd], accumulate=True) for h in range(heads)])
+                ds32 = torch.empty((B, heads, H), dtype=torch.float32, device=dev)
+                dqt16 = torch.empty((B, heads * D), dtype=_BF16, device=dev)
+                with _span("hist_last_bwd"):
+                    _native.check(lib.tt_history_last_bwd1(x16.data_ptr(), x16.stride(0), dz32.data_ptr(), p32.data_ptr(), B, H, D,
+                                                           heads, ds32.data_ptr(), dqt16.data_ptr(), _stream()), "history_last_bwd1")
+                dq0_16 = torch.empty((B, D8), dtype=_BF16, device=dev)
+                gemm_batched([dict(A=dqt16[:, h * D:(h + 1) * D], B=in_w16[D + h * hd:D + (h + 1) * hd], M=B, N=hd, K=D, alpha=c,
+                                   out16=dq0_16[:, h * hd:(h + 1) * hd], colsum=d_in_b[h * hd:(h + 1) * hd]) for h in range(heads)])
+                gemm_batched([dict(A=q0_16[:, h * hd:(h + 1) * hd], B=dqt16[:, h * D:(h + 1) * D], M=hd, N=D, K=B, a_mn=True, b_mn=True,
+                                   alpha=c, out32=d_in_w[D + h * hd:D + (h + 1) * hd], accumulate=True) for h in range(heads)])
+                x0 = x16.view(B, H, D8)[:, 0]
+                gemm(dq0_16, x0, D, D, B, a_mn=True, b_mn=True, out32=d_in_w[:D], accumulate=True)
+                extra32 = torch.empty((B, D), dtype=torch.float32, device=dev)
+                gemm(dq0_16, in_w16[:D], B, D, D, b_mn=True, out32=extra32)  # d q0 Wq: lands on row 0 of every sequence
+                dx16 = torch.empty((B * H, D8), dtype=_BF16, device=dev)
+                dy_sum = torch.zeros(D, dtype=torch.float32, device=dev)  # bias gradient of the layer below
+                with _span("hist_last_bwd"):
+                    _native.check(lib.tt_history_last_bwd2(dz32.data_ptr(), qt32.data_ptr(), p32.data_ptr(), ds32.data_ptr(),
+                                                           extra32.data_ptr(), B, H, D, heads, dx16.data_ptr(), dx16.stride(0),
+                                                           dy_sum.data_ptr(), _stream()), "history_last_bwd2")
+                grads[4 * l: 4 * l + 4] = [d_in_w, d_in_b, d_out_w, d_out_b]
+                dy16 = dx16
+                continue
+            x16, qkv16, o16, in_w16, out_w16 = saved[5 * l: 5 * l + 5]
             q_rows = 1 if last else H
             rows = B * q_rows
             d_out_w = torch.zeros((D, D), dtype=torch.float32, device=dev)
@@ -898,6 +970,7 @@ def tower_forward_fused(towers) -> None:
     _maybe_check_ids(towers[0]["feats"].device, "gather_rows")
 
 
+_HISTORY_LAST_FAST = os.environ.get("TT_B200_HISTORY_LAST_FAST", "1") == "1"  # row-0-only last encoder layer (history_last.cu)
 _FUSED_TOWER_BWD = os.environ.get("TT_B200_FUSED_TOWER_BWD", "0") == "1"  # candidate, see csrc/tower_bwd.cu
 
 
