@@ -288,6 +288,12 @@ int tt_inbatch_ce_bwd_parts(const void* U_bf16, int64_t ldu, const void* const* 
                             float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
                             float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Limit the number of SMs the persistent kernels launched AFTER this call size their grids for (0 = all SMs); returns the
+ * previous limit.  Used to leave SMs to a collective that runs beside a kernel: the batch-sharded loss starts the NCCL
+ * reduce-scatter of dV and runs the dU pass on the remaining SMs (a 148-CTA persistent kernel would otherwise wait for the
+ * SMs NCCL holds and finish late by the collective's duration).  Host-side state, not thread safe. */
+int tt_set_sm_limit(int32_t n);
+
 /* ---- last history-encoder layer, query row 0 only ------------------------------------------ */
 
 /* The reference consumes row 0 of the last nn.MultiheadAttention layer only (src/user_history_encoder.py:116).  For a

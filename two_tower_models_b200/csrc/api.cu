@@ -53,14 +53,15 @@ KernelSpan::~KernelSpan() {
   delete r;
 }
 
+static int g_sm_limit = 0;  // tt_set_sm_limit: SMs the persistent kernels may occupy (0 = all)
 int num_sms() {
   static int cached = 0;
-  if (cached > 0) return cached;
+  if (cached > 0) return (g_sm_limit > 0 && g_sm_limit < cached) ? g_sm_limit : cached;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 1;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 1;
   cached = n;
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -275,6 +276,11 @@ int tt_inbatch_ce_loss_fwd(const void* U, int64_t ldu, const void* V, int64_t ld
   TT_CHECK(labels != nullptr && weights != nullptr && loss != nullptr && g != nullptr && g_norm != nullptr, "tt_inbatch_ce_loss_fwd: null argument");
   return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, loss, g, g_norm,
                              ws, (size_t)ws_bytes, S(stream));
+}
+int tt_set_sm_limit(int32_t n) {
+  const int prev = g_sm_limit;
+  g_sm_limit = n > 0 ? n : 0;
+  return prev;
 }
 int tt_history_last_supported(int64_t H, int64_t D, int64_t heads) { return history_last_supported(H, D, heads); }
 int tt_history_last_fwd(const void* x16, int64_t ldx, const float* qt, int64_t B, int64_t H, int64_t D, int64_t heads, void* z16,

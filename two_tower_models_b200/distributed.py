@@ -78,7 +78,7 @@ def _reduce_scatter_sum(full: torch.Tensor, rank: int, world: int, group) -> tor
 _RS_BF16 = __import__("os").environ.get("TT_B200_RS_BF16", "1") == "1"
 
 
-def _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d):
+def _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d):  # group: the (CTA-limited) overlap group
     """Start the reduce-scatter of the items' gradient (async on NCCL's stream) and return a closure that waits for it
     and returns the local fp32 dV [B, d] (bf16 operand copy attached).  By default the bf16 copy travels (half the
     bytes; the tower backward consumes dV as a bf16 operand anyway) - TT_B200_RS_BF16=0 sends fp32."""
@@ -105,7 +105,7 @@ class ShardedInBatchCE(torch.autograd.Function):
     """ce[B_loc] of the local users against the all-gathered items (positives at column row + rank*B_loc)."""
 
     @staticmethod
-    def forward(ctx, U, V, group, kernels):
+    def forward(ctx, U, V, group, kernels, overlap=None):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         B, d = U.shape
         if V.shape != (B, d):
@@ -116,6 +116,7 @@ class ShardedInBatchCE(torch.autograd.Function):
         ce, lse = kernels.ce_forward(U_op, V_all, B, world * B, d, rank * B)
         ctx.save_for_backward(U_op, V_all, lse)
         ctx.meta = (B, d, rank, world, group, kernels)
+        ctx.overlap = overlap if overlap is not None else (group, 0)
         return ce
 
     @staticmethod
@@ -124,13 +125,15 @@ class ShardedInBatchCE(torch.autograd.Function):
         B, d, rank, world, group, kernels = ctx.meta
         g = g.contiguous().float()
         if hasattr(kernels, "ce_backward_dv") and dist.get_backend(group) != "gloo":
+            og, octas = ctx.overlap
             dV_all, dV_all16 = kernels.ce_backward_dv(U_op, V_all, B, world * B, d, rank * B, lse, g)
-            finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d)  # runs beside the dU pass
-            dU = kernels.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g)
-            return dU, finish(), None, None
+            finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, og, d)  # runs beside the dU pass
+            with ops.sm_reserve(octas):
+                dU = kernels.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g)
+            return dU, finish(), None, None, None
         dU, dV_all = kernels.ce_backward(U_op, V_all, B, world * B, d, rank * B, lse, g)
         dV = _reduce_scatter_sum(dV_all, rank, world, group)
-        return dU, dV, None, None
+        return dU, dV, None, None, None
 
 
 class ShardedWeightedLoss(torch.autograd.Function):
@@ -139,7 +142,7 @@ class ShardedWeightedLoss(torch.autograd.Function):
     a one-thread kernel that folds them into the global loss and the scalar the backward kernels multiply into g."""
 
     @staticmethod
-    def forward(ctx, U, V, labels, weights, group):
+    def forward(ctx, U, V, labels, weights, group, overlap=None):
         from . import _native
 
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -170,6 +173,7 @@ class ShardedWeightedLoss(torch.autograd.Function):
                                                  ops._stream()), "sharded_loss_finalize")
         ctx.save_for_backward(U_op, V_all, lse, g, g_norm)
         ctx.meta = (B, d, rank, world, group)
+        ctx.overlap = overlap if overlap is not None else (group, 0)
         return loss
 
     @staticmethod
@@ -178,10 +182,12 @@ class ShardedWeightedLoss(torch.autograd.Function):
         B, d, rank, world, group = ctx.meta
         gs = ops._f32c(dloss).reshape(1)
         K = _CudaKernels
+        og, octas = ctx.overlap
         dV_all, dV_all16 = K.ce_backward_dv(U_op, V_all, B, world * B, d, rank * B, lse, g, g_scale=gs, g_scale2=g_norm)
-        finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, group, d)  # runs beside the dU pass
-        dU = K.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g, g_scale=gs, g_scale2=g_norm)
-        return dU, finish(), None, None, None
+        finish = _start_reduce_scatter_dv(dV_all, dV_all16, rank, world, og, d)  # runs beside the dU pass
+        with ops.sm_reserve(octas):
+            dU = K.ce_backward_du(U_op, V_all, B, world * B, d, rank * B, lse, g, g_scale=gs, g_scale2=g_norm)
+        return dU, finish(), None, None, None, None
 
 
 class _PeerItemBuffers:
@@ -319,6 +325,25 @@ class DataParallelContext:
         self.peer_memory = bool(peer_memory) and kernels is None
         self._peers = None
         self._row_exchange = None
+        # Communicator for the collective that runs BESIDE a kernel (reduce-scatter of dV during the dU pass): limited to a
+        # few CTAs, and the dU pass leaves that many SMs free (ops.sm_reserve) - with NCCL's default CTA count the 148-CTA
+        # persistent kernel waits for the SMs NCCL holds and its tail grows by the collective's duration.
+        self.overlap_group, self.overlap_ctas = group, 0
+        import os as _os
+
+        # Measured on 8 GPUs (profiles/r02_summary.md): 0 / 16 / 32 CTAs give 1.103 / 1.107 / 1.138 ms per step - the tail of
+        # the dU kernel shrinks (307 -> 267 us) but the slower collective takes it back, so the default stays off.
+        ctas = int(_os.environ.get("TT_B200_RS_CTAS", "0"))
+        if kernels is None and ctas > 0 and dist.get_backend(group) == "nccl":
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = ctas
+                opts.config.min_ctas = 1
+                ranks = dist.get_process_group_ranks(group) if group is not None else None
+                self.overlap_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+                self.overlap_ctas = ctas
+            except Exception:  # older torch / NCCL: keep the main group, no SM reservation
+                self.overlap_group, self.overlap_ctas = group, 0
 
     def compute_training_loss(self, model, user_embedding, item_embeddings, position, labels):
         """Sharded version of TwoTowerBaseRetrieval.compute_training_loss (reference :279-347); the
@@ -337,8 +362,10 @@ class DataParallelContext:
                     and labels.dim() == 2 and labels.shape[1] == model.user_value_weights.shape[0]
                     and not labels.requires_grad and user_embedding.shape[0] <= 65536):
                 # identity hook: weights, batch max and the weighted mean ride in the CE's merge kernel on every rank
-                return ShardedWeightedLoss.apply(user_embedding, item_embeddings, labels, model.user_value_weights, self.group)
-            ce = ShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self.kernels)  # [B_loc]
+                return ShardedWeightedLoss.apply(user_embedding, item_embeddings, labels, model.user_value_weights, self.group,
+                                                 (self.overlap_group, self.overlap_ctas))
+            ce = ShardedInBatchCE.apply(user_embedding, item_embeddings, self.group, self.kernels,
+                                        (self.overlap_group, self.overlap_ctas))  # [B_loc]
         net_user_value = torch.sum(labels * model.user_value_weights, dim=-1)
         net_user_value, additional_loss = model.debias_net_user_value(
             net_user_value=net_user_value, position=position, user_embedding=user_embedding

@@ -74,6 +74,25 @@ def profile_report() -> dict:
     return out
 
 
+class sm_reserve:
+    """Context manager: the persistent kernels enqueued inside size their grids for `reserve` fewer SMs (left to a
+    collective running beside them)."""
+
+    def __init__(self, reserve: int):
+        self.reserve = int(reserve)
+
+    def __enter__(self):
+        if self.reserve > 0:
+            sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            self.prev = _native.lib().tt_set_sm_limit(max(sms - self.reserve, 1))
+        return self
+
+    def __exit__(self, *exc):
+        if self.reserve > 0:
+            _native.lib().tt_set_sm_limit(self.prev)
+        return False
+
+
 def launch_count() -> int:
     """Kernels launched by libtt_b200.so in this process so far."""
     return int(_native.lib().tt_launch_count())
