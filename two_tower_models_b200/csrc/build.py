@@ -26,6 +26,8 @@ if os.environ.get("TT_CE_BWD_LEAN") == "1":  # candidate epilogue of the CE back
     FLAGS.append("-DTT_CE_BWD_LEAN")
 if os.environ.get("TT_CE_POLY") == "1":  # every fourth exponential of the v3 CE backward on the FMA pipe (ce_bwd3.cu)
     FLAGS.append("-DTT_CE_POLY")
+if os.environ.get("TT_CE_FWD_POLY") == "1":  # every fourth exponential of the CE forward on the FMA pipe
+    FLAGS.append("-DTT_CE_FWD_POLY")
 if os.environ.get("TT_CE3_CW"):  # score columns per epilogue thread of the v3 CE backward (16 -> 24 epilogue warps)
     FLAGS.append("-DTT_CE3_CW=" + os.environ["TT_CE3_CW"])
 if os.environ.get("TT_CE_BRINGUP") == "1":  # clock64 timelines / partial epilogues of the CE kernels (tools/trace_ce.py)

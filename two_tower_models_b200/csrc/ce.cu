@@ -265,8 +265,17 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
         } else
 #endif
         {
+#ifdef TT_CE_FWD_POLY
+          // every fourth exponential on the FMA pipe (the forward epilogue is MUFU-bound: XU 71 %, tensor 34 %)
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            const float y = fmaf(x[i], LOG2E, -ms);
+            x[i] = (i & 3) == 3 ? exp2_poly3(y) : ex2f(y);
+          }
+#else
 #pragma unroll
           for (int i = 0; i < CW; ++i) x[i] = ex2f(fmaf(x[i], LOG2E, -ms));
+#endif
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -547,6 +556,13 @@ static bool use_bwd_v3() {
 }
 // columns of Y per score tile of the backward kernels
 static int bwd_tile_cols(int DP, bool v3) { return (v3 && DP <= 128) ? ce_bwd3_tile_cols(DP) : (DP == 256 ? 64 : 128); }
+// ghost tiles per row tile (ce_common.cuh: SegIter): what a row-tile boundary inside a CTA's range costs the v3 kernels
+// (accumulator drain at ~32 B/clk + pipeline refill = ~4 tiles, profiles/r02_ce_bwd3_timeline_*.txt)
+static int bwd_ghost(int DP, bool v3) {
+  static const int g = getenv("TT_CE_BWD_GHOST") ? atoi(getenv("TT_CE_BWD_GHOST")) : 4;
+  return (v3 && DP <= 128) ? g : 0;
+}
+static Sched bwd_sched(long long xr, long long yr, int DP, bool v3) { return make_sched(xr, yr, bwd_tile_cols(DP, v3), bwd_ghost(DP, v3)); }
 
 // forward / backward partials (sized for either backward kernel generation); the v3 backward's ext block (bias rows +
 // sign words of the users) follows at this offset
@@ -556,9 +572,8 @@ static size_t ce_ws_base(long long B, long long N, long long d) {
   size_t best = fwd_ws_bytes(make_sched(B, N, 128), Bpad);
   size_t bmax = 0, cmax = 0;  // the two backward passes use disjoint regions: [dU partials | dV partials]
   for (int v3 = 0; v3 < 2; ++v3) {
-    const int BNb = bwd_tile_cols(DP, v3 != 0);
-    const size_t b = (bwd_ws_bytes(make_sched(B, N, BNb), DP) + 255) / 256 * 256;
-    const size_t c = bwd_ws_bytes(make_sched(N, B, BNb), DP);
+    const size_t b = (bwd_ws_bytes(bwd_sched(B, N, DP, v3 != 0), DP) + 255) / 256 * 256;
+    const size_t c = bwd_ws_bytes(bwd_sched(N, B, DP, v3 != 0), DP);
     if (b > bmax) bmax = b;
     if (c > cmax) cmax = c;
   }
@@ -669,7 +684,7 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
 // out[row, c] = sum over the slots that touched row's tile; one launch handles up to two results (dU and dV) and
 // optionally accumulates the fp32 column sums of each result (= the bias gradient of the tower Linear above it).
 struct ReduceJob {
-  int rows, d, CT;
+  int rows, d, CT, CTr;  // CT = column tiles per row tile including ghost tiles (SegIter), CTr = real ones
   long long T, slot_stride;
   const float* partial;
   float* out32;
@@ -692,7 +707,7 @@ ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
   for (int which = 0; which < 2; ++which) {
     const ReduceJob& j = which ? j1 : j0;
     if (j.blocks == 0) continue;
-    const int T = (int)j.T, CT = j.CT;
+    const int T = (int)j.T, CT = j.CT, CTr = j.CTr;
     const bool vec32 = j.out32 != nullptr && (j.ld32 % 4) == 0 && c + 3 < j.d;
     const bool vec16 = j.out16 != nullptr && (j.ld16 % 4) == 0 && c + 3 < j.d;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -701,7 +716,7 @@ ce_bwd_reduce_kernel(const ReduceJob j0, const ReduceJob j1, int DP) {
       const int row = gi * rpb + ry;
       if (row >= j.rows) continue;
       const int r = row >> 7;
-      const int nsl = (int)((((long long)r + 1) * CT - 1) / T) - (int)(((long long)r * CT) / T);  // last - first slot
+      const int nsl = (int)(((long long)r * CT + CTr - 1) / T) - (int)(((long long)r * CT) / T);  // last - first slot
       const float* src = j.partial + (long long)row * DP + c;
       float4 acc = *reinterpret_cast<const float4*>(src);
       for (int sl = 1; sl <= nsl; ++sl) {
@@ -748,7 +763,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
                        ReduceJob& job, cudaStream_t stream, const void* ext = nullptr) {
   const bool v3 = ext != nullptr && DP <= 128 && (nyp == 1 || ce_bwd3_tile_cols(DP) == 128);  // (96-row tiles would straddle parts)
   const int BN = bwd_tile_cols(DP, v3);
-  const Sched s = make_sched(xr, yr, BN);
+  const Sched s = bwd_sched(xr, yr, DP, v3);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
   CeBwdArgs a;
   a.XR = (int)xr; a.YR = (int)yr; a.diag_shift = diag_shift;
@@ -769,7 +784,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
   if (rc) return rc;
   if (v3) {  // statistics inside the score MMA (ce_bwd3.cu)
     CeBwd3Args b;
-    b.XR = a.XR; b.YR = a.YR; b.diag_shift = a.diag_shift; b.T = a.T; b.total = a.total; b.CT = a.CT;
+    b.XR = a.XR; b.YR = a.YR; b.diag_shift = a.diag_shift; b.T = a.T; b.total = a.total; b.CT = a.CT; b.CTr = s.CTr;
     b.g = g; b.g_scale = g_scale; b.g_scale2 = g_scale2; b.lse = lse; b.signmask = nullptr;
     b.partial = a.partial; b.slot_stride = a.slot_stride; b.trace = a.trace; b.cta_times = a.cta_times;
     b.trace_cta = getenv("TT_CE_TRACE_CTA") ? atoi(getenv("TT_CE_TRACE_CTA")) : 0;
@@ -778,7 +793,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
     rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
   }
   if (rc) return rc;
-  job.rows = (int)xr; job.d = (int)d; job.CT = s.CT; job.T = s.T; job.slot_stride = a.slot_stride;
+  job.rows = (int)xr; job.d = (int)d; job.CT = s.CT; job.CTr = s.CTr; job.T = s.T; job.slot_stride = a.slot_stride;
   job.partial = a.partial; job.out32 = out32; job.ld32 = ld32; job.out16 = (bf16*)out16; job.ld16 = ld16;
   job.colsum = colsum;
   job.blocks = (int)((xr * (DP / 4) + 255) / 256);
@@ -809,7 +824,7 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
   const bool v3 = use_bwd_v3() && DP <= 128;
   size_t offB = 0;  // region of the dV pass: behind the larger of the two possible dU geometries
   for (int k = 0; k < 2; ++k) {
-    const size_t o = (bwd_ws_bytes(make_sched(B, N, bwd_tile_cols(DP, k != 0)), DP) + 255) / 256 * 256;
+    const size_t o = (bwd_ws_bytes(bwd_sched(B, N, DP, k != 0), DP) + 255) / 256 * 256;
     if (o > offB) offB = o;
   }
   ReduceJob ja, jb;

@@ -173,7 +173,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
 
   if (warp == W_TMA) {
     if (lane == 0) {
-      SegIter it(a.T, a.total, a.CT);
+      SegIter it(a.T, a.total, a.CT, a.CTr);
       int r, j0, j1, stage = 0;
       uint32_t phase = 0, xs = 0;
       while (it.next(r, j0, j1)) {
@@ -206,7 +206,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     // succeeds and the thread never blocks.
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);
-    SegIter it(a.T, a.total, a.CT);
+    SegIter it(a.T, a.total, a.CT, a.CTr);
     int r, j0, j1;
     uint32_t t1 = 0, xs = 0;
     const uint64_t dy0 = make_smem_desc_sw128(smem_u32(sy), 0, 1024);
@@ -245,7 +245,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     // ---- issuer of  acc += E Y  (E from its TMEM buffer, Y read MN-major); its completion frees the Y stage and E buffer ----
     const uint32_t leader = elect_one();
     constexpr uint32_t idesc2 = make_idesc_bf16(128, DP, 0, 1);
-    SegIter it(a.T, a.total, a.CT);
+    SegIter it(a.T, a.total, a.CT, a.CTr);
     int r, j0, j1;
     uint32_t t2 = 0, xs = 0;
     const uint64_t dyt0 = make_smem_desc_sw128(smem_u32(sy), BN * 128, 1024);
@@ -280,7 +280,7 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
     const float gabs = fabsf(gsv);
     const float c0 = log2f(gabs);  // -inf for a zero scale: every exponential becomes 0
     const uint32_t sgn_gs = gsv < 0.f ? 0x80008000u : 0u;
-    SegIter it(a.T, a.total, a.CT);
+    SegIter it(a.T, a.total, a.CT, a.CTr);
     int r, j0, j1;
     uint32_t t = 0, xs = 0;
     // X tile (and the bias step of its rows) from shared memory into tensor memory

@@ -7,33 +7,58 @@ namespace tt {
 static constexpr float LOG2E = 1.4426950408889634f;
 static constexpr float LN2 = 0.6931471805599453f;
 
+// Walks the contiguous range of (row tile, column tile) work items of one CTA, segment by segment (a segment = the part
+// of the range inside one row tile).  The flattened space may carry `CT - CTr` GHOST column tiles at the end of every row
+// tile: they are never executed, so a CTA whose range crosses a row-tile boundary (and pays for an accumulator drain and
+// a pipeline refill there) gets that many fewer real tiles than one that does not.
+#ifdef __CUDACC__
+// exp2 on the FMA/ALU pipes (degree-3 minimax of 2^f on [-0.5, 0.5], relative error 7.5e-5): offloads a share of the
+// exponentials from the MUFU pipe (16/clk/SM), see tools/micro/mufu_bench.cu.  x <= 0 in the CE kernels; x < -126 -> ~0.
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517166f, 0.24261112f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992807f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#endif
+
 struct SegIter {
   long long f, f1;
-  int CT;
-  __device__ SegIter(long long T, long long total, int ct) {
+  int CT, CTr;
+  __device__ SegIter(long long T, long long total, int ct, int ctr = -1) {
     f = (long long)blockIdx.x * T;
     f1 = f + T < total ? f + T : total;
     CT = ct;
+    CTr = ctr < 0 ? ct : ctr;
   }
   __device__ bool next(int& r, int& j0, int& j1) {
-    if (f >= f1) return false;
-    r = (int)(f / CT);
-    j0 = (int)(f % CT);
-    long long rem = f1 - f;
-    j1 = (long long)j0 + rem < CT ? (int)(j0 + rem) : CT;
-    f += j1 - j0;
-    return true;
+    while (f < f1) {
+      r = (int)(f / CT);
+      j0 = (int)(f % CT);
+      long long rem = f1 - f;
+      j1 = (long long)j0 + rem < CT ? (int)(j0 + rem) : CT;
+      f += j1 - j0;
+      if (j0 >= CTr) continue;  // only ghost tiles of this row tile
+      if (j1 > CTr) j1 = CTr;
+      return true;
+    }
+    return false;
   }
 };
 
 struct Sched {
   long long T, total;
-  int XT, CT, max_slots, grid;
+  int XT, CT, CTr, max_slots, grid;  // CT = column tiles per row tile INCLUDING ghosts, CTr = real ones
 };
-static inline Sched make_sched(long long x_rows, long long y_rows, int BN) {
+static inline Sched make_sched(long long x_rows, long long y_rows, int BN, int ghost = 0) {
   Sched s;
   s.XT = (int)((x_rows + 127) / 128);
-  s.CT = (int)((y_rows + BN - 1) / BN);
+  s.CTr = (int)((y_rows + BN - 1) / BN);
+  if ((long long)s.XT * s.CTr < 16LL * num_sms()) ghost = 0;  // short ranges: nothing to balance
+  s.CT = s.CTr + ghost;
   s.total = (long long)s.XT * s.CT;
   s.grid = (int)(s.total < num_sms() ? s.total : num_sms());
   s.T = (s.total + s.grid - 1) / s.grid;
@@ -82,7 +107,7 @@ struct CeBwd3Args {
   int XR, YR;
   long long diag_shift;
   long long T, total;
-  int CT;
+  int CT, CTr;               // column tiles per row tile with / without the ghost tiles (see SegIter)
   const float* g;            // upstream dL/dce, indexed by user (any sign)
   const float* g_scale;      // optional device scalars multiplied into g, or null
   const float* g_scale2;
