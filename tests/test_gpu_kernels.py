@@ -170,6 +170,7 @@ CE_CASES = [
     (200, 456, 256, 101),
     (1024, 1024, 256, 0),
     (2048, 2048, 128, 0),
+    (2048, 2048, 256, 0),     # d = 256: the shared-memory-operand variant of the backward, several tiles per CTA
     (128, 32768, 128, 4096),  # few users against many (all-gathered) items: the dV pass walks several row tiles per CTA
     (4096, 160, 64, 0) if False else (96, 20000, 64, 77),
 ]
@@ -292,3 +293,34 @@ def test_inbatch_ce_full_size_properties():
     P[torch.arange(5000, 5512), torch.arange(512)] -= 1.0
     dV_ref = (P / B).t() @ U.double()
     assert_close_fro(dV[csl], dV_ref, rtol=4e-3, what="dV slice")
+
+
+def test_inbatch_ce_config5_shape_slices():
+    """BASELINE configs[4] per-rank shape: 8192 local users against 65 536 all-gathered items at d = 256, positives at
+    column row + 3 * 8192 (rank 3 of 8).  Checked on slices against the fp64 definition: ce / lse and dU of 512 users
+    (full rows of S), dV of 256 items (all 8192 users; the row statistics are the device's own lse, pinned by the first check)."""
+    from two_tower_models_b200 import ops
+
+    B, N, d, off = 8192, 65536, 256, 3 * 8192
+    U, V = _ce_inputs(B, N, d, 123, scale=0.3)
+    dev = _dev()
+    U16, V16 = ops.cast_rows_bf16(U.to(dev)), ops.cast_rows_bf16(V.to(dev))
+    ce, lse = ops.inbatch_ce_forward_raw(U16, V16, B, N, d, off)
+    sl = slice(2048, 2560)
+    ce_ref, lse_ref = oracle.inbatch_ce(U[sl].double(), V.double(), off + 2048)
+    assert float((lse[sl].cpu().double() - lse_ref).abs().max()) < 1e-4
+    assert float((ce[sl].cpu().double() - ce_ref).abs().max()) < 1e-4
+    g = (torch.rand(B, generator=torch.Generator().manual_seed(9)) + 0.5) / N
+    dU, dV, _, _ = ops.inbatch_ce_backward_raw(U16, V16, B, N, d, off, lse, g.to(dev))
+    torch.cuda.synchronize()
+    dU_ref, _ = oracle.inbatch_ce_backward(U[sl].double(), V.double(), lse_ref, g[sl].double(), off + 2048)
+    assert_close_fro(dU[sl], dU_ref, rtol=4e-3, what="dU slice")
+    csl = slice(off + 5000, off + 5256)  # items whose positives are users 5000..5255
+    lse64 = lse.cpu().double()
+    P = torch.exp(U.double() @ V[csl].double().t() - lse64[:, None])
+    P[torch.arange(5000, 5256), torch.arange(256)] -= 1.0
+    dV_ref = (P * g.double()[:, None]).t() @ U.double()
+    assert_close_fro(dV[csl], dV_ref, rtol=4e-3, what="dV slice (items with positives)")
+    csl2 = slice(100, 356)  # items of another rank: no positives among the local users
+    P2 = torch.exp(U.double() @ V[csl2].double().t() - lse64[:, None])
+    assert_close_fro(dV[csl2], (P2 * g.double()[:, None]).t() @ U.double(), rtol=4e-3, what="dV slice (foreign items)")

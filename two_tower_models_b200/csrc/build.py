@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "gemm.cu", "ce.cu", "ce_bwd2.cu", "ce_bwd3.cu", "elementwise.cu", "mips.cu", "attn.cu", "attn_tc.cu", "history_last.cu", "tower.cu", "tower_bwd.cu"]  # missing files are skipped
+SOURCES = ["api.cu", "gemm.cu", "ce.cu", "ce_bwd2.cu", "ce_bwd3.cu", "ce_bwd3x.cu", "elementwise.cu", "mips.cu", "attn.cu", "attn_tc.cu", "history_last.cu", "tower.cu", "tower_bwd.cu"]  # missing files are skipped
 HEADERS = ["common.cuh", "ce_common.cuh", "kernels.h", os.path.join(ROOT, "include", "tt_b200.h")]
 LIB = os.environ.get("TT_B200_LIB_OUT") or os.path.join(HERE, "libtt_b200.so")  # bring-up builds go to another file
 VARIANT = os.path.splitext(os.path.basename(LIB))[0]

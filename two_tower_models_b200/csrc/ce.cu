@@ -560,7 +560,12 @@ static int bwd_tile_cols(int DP, bool v3) { return (v3 && DP <= 128) ? ce_bwd3_t
 // (accumulator drain at ~32 B/clk + pipeline refill = ~4 tiles, profiles/r02_ce_bwd3_timeline_*.txt)
 static int bwd_ghost(int DP, bool v3) {
   static const int g = getenv("TT_CE_BWD_GHOST") ? atoi(getenv("TT_CE_BWD_GHOST")) : 4;
-  return (v3 && DP <= 128) ? g : 0;
+  return v3 ? g : 0;
+}
+// the d = 256 variant of the v3 kernels (ce_bwd3x.cu) unless TT_CE_BWD_V3X=0
+static bool use_bwd_v3x() {
+  static const bool on = !(getenv("TT_CE_BWD_V3X") && atoi(getenv("TT_CE_BWD_V3X")) == 0);
+  return on;
 }
 static Sched bwd_sched(long long xr, long long yr, int DP, bool v3) { return make_sched(xr, yr, bwd_tile_cols(DP, v3), bwd_ghost(DP, v3)); }
 
@@ -761,7 +766,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
                        const float* g_scale2, const float* lse, float* out32,
                        long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
                        ReduceJob& job, cudaStream_t stream, const void* ext = nullptr) {
-  const bool v3 = ext != nullptr && DP <= 128 && (nyp == 1 || ce_bwd3_tile_cols(DP) == 128);  // (96-row tiles would straddle parts)
+  const bool v3 = ext != nullptr && (DP == 256 || nyp == 1 || ce_bwd3_tile_cols(DP) == 128);  // (96-row tiles would straddle parts)
   const int BN = bwd_tile_cols(DP, v3);
   const Sched s = bwd_sched(xr, yr, DP, v3);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
@@ -788,7 +793,8 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
     b.g = g; b.g_scale = g_scale; b.g_scale2 = g_scale2; b.lse = lse; b.signmask = nullptr;
     b.partial = a.partial; b.slot_stride = a.slot_stride; b.trace = a.trace; b.cta_times = a.cta_times;
     b.trace_cta = getenv("TT_CE_TRACE_CTA") ? atoi(getenv("TT_CE_TRACE_CTA")) : 0;
-    rc = launch_ce_bwd3(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream);
+    rc = DP == 256 ? launch_ce_bwd3x(!colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream)
+                   : launch_ce_bwd3(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream);
   } else {
     rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
   }
@@ -821,7 +827,7 @@ int inbatch_ce_bwd_parts(const void* U, long long ldu, const void* const* Vp, in
            "inbatch_ce_bwd: operands need 16-byte aligned rows");
   TT_CHECK(ws_bytes >= inbatch_ce_workspace_bytes(B, N, d), "inbatch_ce_bwd: workspace too small");
   const int DP = pick_dp(d);
-  const bool v3 = use_bwd_v3() && DP <= 128;
+  const bool v3 = use_bwd_v3() && (DP <= 128 || use_bwd_v3x());
   size_t offB = 0;  // region of the dV pass: behind the larger of the two possible dU geometries
   for (int k = 0; k < 2; ++k) {
     const size_t o = (bwd_ws_bytes(bwd_sched(B, N, DP, k != 0), DP) + 255) / 256 * 256;

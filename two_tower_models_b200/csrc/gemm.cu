@@ -339,7 +339,7 @@ static int launch_gemm(const GemmBatch& bt, cudaStream_t stream) {
   return 0;
 }
 
-static int pick_bn(const GemmDesc& d) {
+static int pick_bn(const GemmDesc& d, int share = 1) {
   // fewest padded columns first; then the widest tile that still gives ~one CTA per SM, else the narrowest
   int BN = 64;
   const long long m_tiles = (d.M + BM - 1) / BM;
@@ -354,7 +354,7 @@ static int pick_bn(const GemmDesc& d) {
     const long long padded = (d.N + cand[i] - 1) / cand[i] * cand[i];
     if (padded != best_pad) continue;
     BN = cand[i];  // ends at the narrowest candidate with minimal padding
-    if (m_tiles * (padded / cand[i]) * 4 >= 3ll * num_sms()) found = true;
+    if (m_tiles * (padded / cand[i]) * share * 4 >= 3ll * num_sms()) found = true;  // share = problems in the launch
   }
   return BN;
 }
@@ -418,9 +418,15 @@ int gemm_bf16_batched(const GemmDesc* d, int n, cudaStream_t stream) {
   TT_CHECK(n >= 1, "gemm: empty batch");
   int i = 0;
   while (i < n) {  // greedy groups of consecutive problems with the same tile width and accumulation mode
-    const int BN = pick_bn(d[i]);
+    // tile width chosen for the whole group: identical problems batched into one launch (the same layer of both towers)
+    // together fill the SMs with wider tiles than each would alone
+    int same = 1;
+    while (i + same < n && same < MAXP && d[i + same].M == d[i].M && d[i + same].N == d[i].N && d[i + same].K == d[i].K &&
+           (d[i + same].accumulate != 0) == (d[i].accumulate != 0))
+      ++same;
+    const int BN = pick_bn(d[i], same);
     int j = i + 1;
-    while (j < n && j - i < MAXP && pick_bn(d[j]) == BN && (d[j].accumulate != 0) == (d[i].accumulate != 0)) ++j;
+    while (j < n && j - i < MAXP && pick_bn(d[j], same) == BN && (d[j].accumulate != 0) == (d[i].accumulate != 0)) ++j;
     GemmBatch bt;
     bt.n = j - i;
     bt.work_start[0] = 0;
