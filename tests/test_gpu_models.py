@@ -249,6 +249,27 @@ def test_overridden_tower_methods_are_dispatched_in_training():
     assert abs(float(loss) - float(ref)) <= LOSS_RTOL * abs(float(ref))
 
 
+def test_out_of_range_ids_raise_index_error():
+    """nn.Embedding raises IndexError on an out-of-range id; the gather kernels clamp and flag, and the flag is surfaced
+    on demand (ops.check_ids) and by the periodic check of the lookups."""
+    from two_tower_models_b200 import ops
+
+    d, F, B = 64, 32, 128
+    p = _random_base_params(d, d, F, F, 300, 300, seed=21)
+    m = _build_base(p, torch.tensor([1.0]))
+    batch = _random_batch(B, F, F, 300, 300, 1, seed=22)
+    ops.check_ids()  # clear
+    batch["user_id"][5] = 300  # == table rows: out of range
+    b = {k: v.cuda() for k, v in batch.items()}
+    with pytest.raises(IndexError):
+        m.train_forward(b["user_id"], b["user_features"], b["user_history"], b["item_id"], b["item_features"],
+                        b["position"], b["labels"])
+        ops.check_ids()
+    ops.check_ids()  # the flag was consumed: a clean lookup afterwards passes
+    m.compute_item_embeddings(b["item_id"], b["item_features"])
+    ops.check_ids()
+
+
 def test_requires_cuda_and_library():
     import two_tower_models_b200 as tt
 

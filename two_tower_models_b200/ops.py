@@ -14,7 +14,13 @@ import torch
 from . import _native
 
 _BF16 = torch.bfloat16
-_CHECK_IDS = os.environ.get("TT_B200_CHECK_IDS", "0") == "1"
+# Out-of-range embedding ids: the gather kernels clamp them and raise a device flag (nn.Embedding raises IndexError).
+# TT_B200_CHECK_IDS=1 reads the flag after EVERY lookup (a host sync per call); by default it is read every
+# _CHECK_IDS_EVERY-th lookup outside stream capture - bad ids surface within a few steps at ~no cost - and on demand
+# through check_ids().  TT_B200_CHECK_IDS=0 turns the periodic check off.
+_CHECK_IDS = os.environ.get("TT_B200_CHECK_IDS", "")
+_CHECK_IDS_EVERY = 64
+_check_ids_calls = 0
 
 
 class KernelTimer:
@@ -214,10 +220,25 @@ def _oob_flag(device) -> torch.Tensor:
     return f
 
 
+def check_ids(device=None, what="embedding lookup") -> None:
+    """Raise IndexError if a lookup since the last check saw an id outside its table (synchronises the device)."""
+    devs = list(_oob_flags) if device is None else [device]
+    for dev in devs:
+        f = _oob_flags.get(dev)
+        if f is not None and int(f.item()) != 0:
+            f.zero_()
+            raise IndexError(f"{what}: index out of range in embedding lookup")
+
+
 def _maybe_check_ids(device, what):
-    if _CHECK_IDS and int(_oob_flag(device).item()) != 0:
-        _oob_flag(device).zero_()
-        raise IndexError(f"{what}: index out of range in embedding lookup")
+    global _check_ids_calls
+    if _CHECK_IDS == "0":
+        return
+    _check_ids_calls += 1
+    if _CHECK_IDS == "1" or _check_ids_calls % _CHECK_IDS_EVERY == 1:
+        if torch.cuda.is_current_stream_capturing():
+            return
+        check_ids(device, what)
 
 
 def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, col_offset: int = 0) -> None:
