@@ -288,6 +288,13 @@ int tt_inbatch_ce_bwd_parts(const void* U_bf16, int64_t ldu, const void* const* 
                             float* dV_f32, int64_t lddv, void* dV_bf16, int64_t lddv16, float* dU_colsum,
                             float* dV_colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The next tt_inbatch_ce_fwd / tt_inbatch_ce_loss_fwd* launch of the calling thread also fills up to two device buffers
+ * with zeros (16-byte aligned, sizes multiples of 16 bytes; p1 may be NULL): an otherwise idle warp of the scoring kernel
+ * streams them out with TMA bulk stores while the score tiles run.  Used for the dense embedding-table gradients of the
+ * training step (the reference's nn.Embedding(sparse=False) semantics: 2 x hash x D floats zero-filled per step), which
+ * would otherwise cost a ~8 us memset between the tower and the scoring kernels. */
+int tt_inbatch_ce_attach_zero_fill(void* p0, int64_t bytes0, void* p1, int64_t bytes1);
+
 /* Limit the number of SMs the persistent kernels launched AFTER this call size their grids for (0 = all SMs); returns the
  * previous limit.  Used to leave SMs to a collective that runs beside a kernel: the batch-sharded loss starts the NCCL
  * reduce-scatter of dV and runs the dU pass on the remaining SMs (a 148-CTA persistent kernel would otherwise wait for the

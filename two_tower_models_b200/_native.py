@@ -112,6 +112,7 @@ SIGNATURES = {
     "tt_inbatch_ce_loss_fwd_sharded": (I32, [P, I64, P, I64, I64, I64, I64, I64, P, I64, P, I64, P, P, P, P, P, I64, P]),
     "tt_sharded_loss_finalize": (I32, [P, I32, I64, P, P, P]),
     "tt_set_sm_limit": (I32, [I32]),
+    "tt_inbatch_ce_attach_zero_fill": (I32, [P, I64, P, I64]),
     "tt_history_last_supported": (I32, [I64, I64, I64]),
     "tt_history_last_fwd": (I32, [P, I64, P, I64, I64, I64, I64, P, P, P]),
     "tt_history_last_bwd1": (I32, [P, I64, P, P, I64, I64, I64, I64, P, P, P]),

@@ -277,6 +277,9 @@ int tt_inbatch_ce_loss_fwd(const void* U, int64_t ldu, const void* V, int64_t ld
   return inbatch_ce_loss_fwd(U, ldu, &V, 1, N, ldv, B, N, d, target_offset, ce, lse, labels, ldl, weights, T, loss, g, g_norm,
                              ws, (size_t)ws_bytes, S(stream));
 }
+int tt_inbatch_ce_attach_zero_fill(void* p0, int64_t bytes0, void* p1, int64_t bytes1) {
+  return inbatch_ce_attach_zero_fill(p0, bytes0, p1, bytes1);
+}
 int tt_set_sm_limit(int32_t n) {
   const int prev = g_sm_limit;
   g_sm_limit = n > 0 ? n : 0;

@@ -39,6 +39,10 @@ struct CeFwdArgs {
   float* part_s;
   struct LossSync* sync;  // ticket of the fused combine+loss kernel, zeroed here
   unsigned skew_ns;       // start delay of the odd epilogue groups
+  // optional zero fills riding in this launch (tt_inbatch_ce_attach_zero_fill): an otherwise idle warp streams zeros
+  // from shared memory with TMA bulk stores while the scoring tiles run
+  uint8_t* zero_ptr[2];
+  long long zero_bytes[2];
   long long* trace;  // bring-up (TT_CE_TRACE)
   int dbg;           // bring-up (TT_CE_DBG): bit0 skip ex2, bit1 skip the maximum, bit2 skip the whole tile update
 };
@@ -55,7 +59,8 @@ struct CeFwdCfg {
   static constexpr int X_BYTES = 128 * DP * 2;
   static constexpr int Y_BYTES = BN * DP * 2;
   static constexpr int STAGES = DP == 64 ? 6 : (DP == 128 ? 4 : 2);
-  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + 1024 + 256;
+  static constexpr int ZERO_BYTES = 16384;  // source of the fused zero fills
+  static constexpr int SMEM_BYTES = X_BYTES + STAGES * Y_BYTES + ZERO_BYTES + 1024 + 256;
 };
 
 // Both epilogue groups work on EVERY score tile, each on one half of its columns (group e: columns
@@ -82,7 +87,8 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sx = smem;
   uint8_t* sy = smem + Cfg::X_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + Cfg::STAGES * Cfg::Y_BYTES);
+  uint8_t* sz = sy + Cfg::STAGES * Cfg::Y_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sz + Cfg::ZERO_BYTES);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 1;
   uint64_t* s_full = bars + 2;
@@ -111,6 +117,11 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_holder, NS * BN);
+  const bool zfill = a.zero_bytes[0] > 0 || a.zero_bytes[1] > 0;
+  if (zfill) {
+    for (int i = threadIdx.x; i < Cfg::ZERO_BYTES / 16; i += FWD_THREADS) reinterpret_cast<uint4*>(sz)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -184,6 +195,24 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ T
         umma_commit_w(x_empty, leader);
         ++xs;
       }
+    }
+  } else if (warp == 3) {
+    // fused zero fills (the dense embedding-table gradients of the step: 2 x 51 MB at the benchmark shape): 16 KB chunks,
+    // CTA-strided, all issued up front - the TMA engine drains them beside the scoring tiles, no SM instruction issue
+    if (zfill && lane == 0) {
+      constexpr long long CH = Cfg::ZERO_BYTES;
+      for (int z = 0; z < 2; ++z) {
+        const long long n = a.zero_bytes[z];
+        for (long long c = blockIdx.x; c * CH < n; c += gridDim.x) {
+          const long long rem = n - c * CH;
+          const uint32_t bytes = (uint32_t)(rem < CH ? rem : CH);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(a.zero_ptr[z] + c * CH), "r"(smem_u32(sz)), "r"(bytes)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= 4) {
     const int e = (warp - 4) >> 2;  // column group of every tile
@@ -503,6 +532,17 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
 
 __global__ void set_scalar_kernel(float* p, float v) { *p = v; }
 
+// zero fills attached to the next forward launch of the calling thread
+static thread_local struct { void* p[2]; long long n[2]; } g_zero_jobs = {{nullptr, nullptr}, {0, 0}};
+int inbatch_ce_attach_zero_fill(void* p0, long long bytes0, void* p1, long long bytes1) {
+  TT_CHECK(((uintptr_t)p0 % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && bytes0 >= 0 && bytes1 >= 0 && bytes0 % 16 == 0 && bytes1 % 16 == 0,
+           "inbatch_ce_attach_zero_fill: buffers need 16-byte alignment and sizes that are multiples of 16 bytes");
+  TT_CHECK(g_zero_jobs.n[0] == 0 && g_zero_jobs.n[1] == 0, "inbatch_ce_attach_zero_fill: zero fills are already pending");
+  g_zero_jobs.p[0] = p0; g_zero_jobs.n[0] = p0 ? bytes0 : 0;
+  g_zero_jobs.p[1] = p1; g_zero_jobs.n[1] = p1 ? bytes1 : 0;
+  return 0;
+}
+
 // Batch-sharded loss: fold the all-gathered per-rank (max nuv, sum ce nuv) pairs into the global weighted mean
 // loss = sum_r s_r / (max_r m_r * rows) and the scalar g_norm = 1 / (max * rows) the backward kernels multiply into g.
 __global__ void sharded_loss_finalize_kernel(const float* __restrict__ stats_all, int world, float inv_rows,
@@ -555,7 +595,15 @@ static bool use_bwd_v3() {
   return on;
 }
 // columns of Y per score tile of the backward kernels
-static int bwd_tile_cols(int DP, bool v3) { return (v3 && DP <= 128) ? ce_bwd3_tile_cols(DP) : (DP == 256 ? 64 : 128); }
+// TT_CE_BWD_X128=1: the d = 128 problem on the shared-memory-operand variant (ce_bwd3x.cu, 128-wide tiles, 16 epilogue warps)
+static bool use_x128() {
+  static const bool on = getenv("TT_CE_BWD_X128") && atoi(getenv("TT_CE_BWD_X128")) != 0;
+  return on;
+}
+static int bwd_tile_cols(int DP, bool v3) {
+  if (v3 && DP == 128 && use_x128()) return 128;
+  return (v3 && DP <= 128) ? ce_bwd3_tile_cols(DP) : (DP == 256 ? 64 : 128);
+}
 // ghost tiles per row tile (ce_common.cuh: SegIter): what a row-tile boundary inside a CTA's range costs the v3 kernels
 // (accumulator drain at ~32 B/clk + pipeline refill = ~4 tiles, profiles/r02_ce_bwd3_timeline_*.txt)
 static int bwd_ghost(int DP, bool v3) {
@@ -642,6 +690,12 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
   dgo.U = (const bf16*)U; dgo.ldu = ldu; dgo.ldv = ldv; dgo.target_offset = target_offset; dgo.d = (int)d;
   dgo.rows_per_part = np == 1 ? N : rows_per_part;
   for (int p = 0; p < 8; ++p) dgo.Vp[p] = (const bf16*)Vp[p < np ? p : 0];
+  for (int z = 0; z < 2; ++z) {  // consume the attached zero fills
+    a.zero_ptr[z] = (uint8_t*)g_zero_jobs.p[z];
+    a.zero_bytes[z] = g_zero_jobs.n[z];
+    g_zero_jobs.p[z] = nullptr;
+    g_zero_jobs.n[z] = 0;
+  }
   a.trace = nullptr;
   if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
   a.dbg = getenv("TT_CE_DBG") ? atoi(getenv("TT_CE_DBG")) : 0;
@@ -766,7 +820,7 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
                        const float* g_scale2, const float* lse, float* out32,
                        long long ld32, void* out16, long long ld16, float* colsum, void* ws, size_t ws_bytes,
                        ReduceJob& job, cudaStream_t stream, const void* ext = nullptr) {
-  const bool v3 = ext != nullptr && (DP == 256 || nyp == 1 || ce_bwd3_tile_cols(DP) == 128);  // (96-row tiles would straddle parts)
+  const bool v3 = ext != nullptr && (DP == 256 || nyp == 1 || bwd_tile_cols(DP, true) == 128);  // (96-row tiles would straddle parts)
   const int BN = bwd_tile_cols(DP, v3);
   const Sched s = bwd_sched(xr, yr, DP, v3);
   TT_CHECK(ws_bytes >= bwd_ws_bytes(s, DP), "inbatch_ce_bwd: workspace too small (%zu < %zu)", ws_bytes, bwd_ws_bytes(s, DP));
@@ -793,8 +847,9 @@ static int ce_bwd_pass(bool colstats, const void* const* Xp, int nxp, long long 
     b.g = g; b.g_scale = g_scale; b.g_scale2 = g_scale2; b.lse = lse; b.signmask = nullptr;
     b.partial = a.partial; b.slot_stride = a.slot_stride; b.trace = a.trace; b.cta_times = a.cta_times;
     b.trace_cta = getenv("TT_CE_TRACE_CTA") ? atoi(getenv("TT_CE_TRACE_CTA")) : 0;
-    rc = DP == 256 ? launch_ce_bwd3x(!colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream)
-                   : launch_ce_bwd3(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream);
+    rc = (DP == 256 || (DP == 128 && use_x128()))
+             ? launch_ce_bwd3x(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream)
+             : launch_ce_bwd3(DP, !colstats, tx, ty, colstats ? yr : xr, ext, b, s.grid, stream);
   } else {
     rc = launch_ce_bwd2(DP, colstats, tx, ty, a, s.grid, stream);
   }

@@ -18,10 +18,10 @@ namespace tt {
 
 namespace {
 
-template <bool BIAS_X>
+template <int DPV, bool BIAS_X>
 struct CfgX {
-  static constexpr int DP = 256;
-  static constexpr int BN = 64;
+  static constexpr int DP = DPV;
+  static constexpr int BN = DPV == 256 ? 64 : 128;  // TMEM: 2 BN + BN + DP <= 512
   static constexpr int NB = 2, NE = 2;
   static constexpr int EG = BN / 32;                                  // 2 column groups x 4 lane quarters
   static constexpr int THREADS = 128 + EG * 128;
@@ -31,7 +31,7 @@ struct CfgX {
   static constexpr int Y_MAIN = BN * DP * 2;                          // 4 K-atoms of 64 rows x 128 B
   static constexpr int EXT_BYTES = BN * 128;
   static constexpr int Y_BYTES = Y_MAIN + (BIAS_X ? 0 : EXT_BYTES);   // dV: the users' bias rows travel with the Y tile
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (DPV == 128 && BIAS_X) ? 5 : 4;
   static constexpr int SMEM_BYTES = X_BYTES + XE_BYTES + ONES_BYTES + STAGES * Y_BYTES + 1024 + 512;
   static constexpr int E_COL = NB * BN;
   static constexpr int ACC_COL = E_COL + NE * (BN / 2);
@@ -39,11 +39,11 @@ struct CfgX {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <bool BIAS_X>
-__global__ void __launch_bounds__(CfgX<BIAS_X>::THREADS, 1)
+template <int DPV, bool BIAS_X>
+__global__ void __launch_bounds__(CfgX<DPV, BIAS_X>::THREADS, 1)
 ce_bwd3x_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ TmapSet tmy,
                 const __grid_constant__ CUtensorMap tme, const CeBwd3Args a) {
-  using Cfg = CfgX<BIAS_X>;
+  using Cfg = CfgX<DPV, BIAS_X>;
   constexpr int DP = Cfg::DP, BN = Cfg::BN, EG = Cfg::EG, NB = Cfg::NB, NE = Cfg::NE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -321,16 +321,16 @@ ce_bwd3x_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tma
   }
 }
 
-template <bool BIAS_X>
+template <int DPV, bool BIAS_X>
 int launch3x(const TmapSet& tx, const TmapSet& ty, const CUtensorMap& te, const CeBwd3Args& a, int grid, cudaStream_t st) {
-  using Cfg = CfgX<BIAS_X>;
+  using Cfg = CfgX<DPV, BIAS_X>;
   static bool configured = false;
   if (!configured) {
-    TT_CUDA(cudaFuncSetAttribute(ce_bwd3x_kernel<BIAS_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    TT_CUDA(cudaFuncSetAttribute(ce_bwd3x_kernel<DPV, BIAS_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   KernelSpan span(BIAS_X ? "ce_bwd3x_kernel_dU" : "ce_bwd3x_kernel_dV", st);
-  ce_bwd3x_kernel<BIAS_X><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tx, ty, te, a);
+  ce_bwd3x_kernel<DPV, BIAS_X><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tx, ty, te, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -338,14 +338,15 @@ int launch3x(const TmapSet& tx, const TmapSet& ty, const CUtensorMap& te, const 
 
 }  // namespace
 
-int launch_ce_bwd3x(bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext, CeBwd3Args a,
+int launch_ce_bwd3x(int DP, bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext, CeBwd3Args a,
                     int grid, cudaStream_t st) {
   const long long pad = (users + 127) / 128 * 128;
   a.signmask = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ext) + (size_t)pad * 128);
   CUtensorMap te;
-  int rc = make_tmap_bf16(&te, ext, 64, (uint64_t)pad, 64, 64, 64);
+  int rc = make_tmap_bf16(&te, ext, 64, (uint64_t)pad, 64, 64, DP == 256 ? 64 : 128);
   if (rc) return rc;
-  return bias_x ? launch3x<true>(tx, ty, te, a, grid, st) : launch3x<false>(tx, ty, te, a, grid, st);
+  if (DP == 128) return bias_x ? launch3x<128, true>(tx, ty, te, a, grid, st) : launch3x<128, false>(tx, ty, te, a, grid, st);
+  return bias_x ? launch3x<256, true>(tx, ty, te, a, grid, st) : launch3x<256, false>(tx, ty, te, a, grid, st);
 }
 
 }  // namespace tt

@@ -124,7 +124,7 @@ int ce_bwd3_tile_cols(int DP);  // columns of Y per score tile (128 at d <= 64, 
 size_t ce_bwd3_ext_bytes(long long users);
 int ce_bwd3_prep(long long users, const float* g, const float* lse, void* ext, cudaStream_t st);
 // 128 < d <= 256 (ce_bwd3x.cu): X operand in shared memory, 128 x 64 score tiles
-int launch_ce_bwd3x(bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext, CeBwd3Args a,
+int launch_ce_bwd3x(int DP, bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext, CeBwd3Args a,
                     int grid, cudaStream_t st);
 int launch_ce_bwd3(int DP, bool bias_x, const TmapSet& tx, const TmapSet& ty, long long users, const void* ext,
                    CeBwd3Args a, int grid, cudaStream_t st);

@@ -50,6 +50,8 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
                         long long ldv, long long B, long long N, long long d, long long target_offset, float* ce,
                         float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
                         float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream, float* stats = nullptr);
+// the next forward launch of the calling thread also zero-fills these buffers (TMA bulk stores from an idle warp)
+int inbatch_ce_attach_zero_fill(void* p0, long long bytes0, void* p1, long long bytes1);
 // stats (optional, [2]): this rank's (max nuv, sum ce nuv) for the batch-sharded loss; merged by sharded_loss_finalize
 int sharded_loss_finalize(const float* stats_all, int world, long long rows, float* loss, float* g_norm, cudaStream_t stream);
 // dU (fp32 [B,d], optional bf16 copy) and dV (fp32 [N,d], optional bf16 copy) from upstream g[B].

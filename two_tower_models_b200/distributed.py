@@ -161,6 +161,7 @@ class ShardedWeightedLoss(torch.autograd.Function):
         stats = torch.empty(4, dtype=torch.float32, device=dev)
         ws = ops._ce_workspace(B, N, d, dev)
         L = _native.lib()
+        ops._attach_pending_zero()  # the dense table-gradient zero fills of the step ride in this launch
         _native.check(
             L.tt_inbatch_ce_loss_fwd_sharded(U_op.data_ptr(), U_op.stride(0), V_all.data_ptr(), V_all.stride(0), B, N, d,
                                              rank * B, labels.data_ptr(), labels.stride(0), weights.data_ptr(),

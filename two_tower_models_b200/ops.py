@@ -549,6 +549,7 @@ def inbatch_ce_forward_raw(U16, V16, B, N, d, target_offset=0):
     ce = torch.empty(B, dtype=torch.float32, device=U16.device)
     lse = torch.empty(B, dtype=torch.float32, device=U16.device)
     ws = _ce_workspace(B, N, d, U16.device)
+    _attach_pending_zero()
     with _span("inbatch_ce_fwd"):
         _native.check(
             _native.lib().tt_inbatch_ce_fwd(U16.data_ptr(), U16.stride(0), V16.data_ptr(), V16.stride(0), B, N, d,
@@ -647,6 +648,7 @@ class InBatchWeightedLossFunction(torch.autograd.Function):
         ce, lse, g, g_norm = out[:B], out[B:2 * B], out[2 * B:3 * B], out[3 * B:]
         loss = torch.empty((), dtype=torch.float32, device=dev)  # its own storage: the caller may modify it in place
         ws = _ce_workspace(B, N, d, dev)
+        _attach_pending_zero()
         with _span("inbatch_ce_fwd"):
             _native.check(
                 _native.lib().tt_inbatch_ce_loss_fwd(
@@ -1047,6 +1049,27 @@ _LATE_ZERO_FILL = os.environ.get("TT_B200_LATE_ZERO_FILL", "1") == "1"
 _pending_fills = []  # (device, event) of side-stream zero fills that the current stream has not joined yet
 
 
+_FUSED_ZERO_FILL = os.environ.get("TT_B200_FUSED_ZERO_FILL", "1") == "1"
+_pending_zero = []  # fp32 buffers waiting for a zero fill that the next in-batch CE forward launch will carry
+
+
+def _attach_pending_zero() -> None:
+    """Hand the waiting zero fills (the dense table gradients of the step) to the CE forward launch that follows: an idle
+    warp of the scoring kernel streams the zeros out with TMA bulk stores (tt_inbatch_ce_attach_zero_fill)."""
+    while _pending_zero:
+        a = _pending_zero.pop()
+        b = _pending_zero.pop() if _pending_zero else None
+        if b is not None and b.device != a.device:
+            _pending_zero.append(b)
+            b = None
+        _native.check(_native.lib().tt_inbatch_ce_attach_zero_fill(
+            a.data_ptr(), a.numel() * 4, _ptr(b), 0 if b is None else b.numel() * 4), "inbatch_ce_attach_zero_fill")
+        if _pending_zero:  # more than two buffers: the rest is filled by plain memsets
+            for t in _pending_zero:
+                t.zero_()
+            _pending_zero.clear()
+
+
 def join_pending_fills() -> None:
     """Make the current stream wait for the dense table-gradient zero fills that TowerSetFunction.forward started on
     the side stream.  train_forward calls this after the loss forward (the fills then ran beside the scoring kernels,
@@ -1054,6 +1077,8 @@ def join_pending_fills() -> None:
     while _pending_fills:
         device, ev = _pending_fills.pop()
         torch.cuda.current_stream(device).wait_event(ev)
+    while _pending_zero:  # no CE forward launch picked them up (a custom loss): plain memsets
+        _pending_zero.pop().zero_()
 
 
 def _stage_weight(packed: PackedWeights, key, param, casts, segments=None) -> torch.Tensor:
@@ -1144,7 +1169,7 @@ class TowerSetFunction(torch.autograd.Function):
                 return cur_, ev_
 
             # data parallel keeps the fills inside this function (the path that was measured on 2 GPUs)
-            late_fill = _LATE_ZERO_FILL and all(spec[1] is None for spec in specs)
+            late_fill = _LATE_ZERO_FILL and (_FUSED_ZERO_FILL or all(spec[1] is None for spec in specs))
             if zero_jobs and not late_fill:
                 cur, ev = start_fills()
             # data parallel, every tower exchanging row-wise through the same object: the ids of ALL towers travel in
@@ -1178,6 +1203,12 @@ class TowerSetFunction(torch.autograd.Function):
                 cur.wait_event(ev)
                 for d in zero_jobs:
                     d["dtable"].record_stream(cur)
+            elif zero_jobs and _FUSED_ZERO_FILL and all((d["table_rows"] * d["D"]) % 4 == 0 for d in zero_jobs):
+                # the fills ride in the in-batch CE forward launch that follows (TMA bulk stores from an idle warp of the
+                # scoring kernel); join_pending_fills() falls back to memsets when no such launch comes
+                for d in zero_jobs:
+                    d["dtable"] = torch.empty((d["table_rows"], d["D"]), dtype=torch.float32, device=d["feats16"].device)
+                    _pending_zero.append(d["dtable"])
             elif zero_jobs:  # fork now; the caller joins after the loss forward (join_pending_fills), else backward does
                 cur, ev = start_fills()
                 _pending_fills.append((cur.device, ev))
