@@ -30,6 +30,11 @@ if os.environ.get("TT_CE_FWD_POLY") == "1":  # every fourth exponential of the C
     FLAGS.append("-DTT_CE_FWD_POLY")
 if os.environ.get("TT_CE3_CW"):  # score columns per epilogue thread of the v3 CE backward (16 -> 24 epilogue warps)
     FLAGS.append("-DTT_CE3_CW=" + os.environ["TT_CE3_CW"])
+for _k in ("TT_MIPS_CW", "TT_MIPS_SLEEP", "TT_MIPS_TRIG"):  # MIPS epilogue experiments: chunk width (16 / 32), sleep (ns) between barrier probes
+    if os.environ.get(_k):
+        FLAGS.append("-D%s=%s" % (_k, os.environ[_k]))
+if os.environ.get("TT_MIPS_BRINGUP") == "1":  # per-tile clock stamps / partial epilogues of the MIPS screen kernel (tools/mips_trace.py)
+    FLAGS.append("-DTT_MIPS_BRINGUP")
 if os.environ.get("TT_CE_BRINGUP") == "1":  # clock64 timelines / partial epilogues of the CE kernels (tools/trace_ce.py)
     FLAGS.append("-DTT_CE_BRINGUP")
 

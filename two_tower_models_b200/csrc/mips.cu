@@ -2,25 +2,35 @@
 //
 // Reference semantics: src/baseline_mips_module.py:57-61 (torch.topk(torch.matmul(query, corpus.T), k)),
 // indices int64, scores sorted descending.  The [Q, C] score matrix (262 GB at BASELINE config 4) never
-// exists: 128 x 256 score tiles are produced by tcgen05.mma into TMEM from TMA-staged bf16 tiles and are
+// exists: 128 x 128 score tiles are produced by tcgen05.mma into TMEM from TMA-staged bf16 tiles and are
 // filtered in place against a per-row running threshold.
 //
-// Three kernels:
-//   1. mips_screen_kernel (persistent, one CTA per SM, 384 threads)
-//        warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator,
-//        warps 4-7 / 8-11: epilogue group 0 / 1.  A CTA holds TWO 128-row query tiles; the corpus tile
-//        stream (256 rows per stage) is shared by both, group e owns the accumulator of query tile e
-//        (TMEM columns [256 e, 256 e + 256)), so every query row belongs to exactly one thread, which keeps
-//        that row's threshold tau in a register and its candidate list (<= 512 packed (score, index) keys)
-//        in an L2-resident scratch area.  Per 32-column chunk the thread reduces its 32 scores with a max
-//        tree and compares once; the rare chunks with a hit are appended warp-cooperatively.  A full list is
-//        cut back to its best `kp` entries by a warp-wide bisection on the score bits (no sort in the scan).
+// Two kernels:
+//   1. mips_screen_kernel (persistent, one CTA per SM, 640 threads)
+//        warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue.
+//        A CTA holds TWO 128-row query tiles; the corpus tile stream (128 rows per stage) is shared by both.
+//        Each query tile has TWO accumulator buffers (2 x 2 x 128 = the 512 TMEM columns), tile t goes to buffer
+//        t mod 2, and each (query tile, buffer, TMEM lane quarter) has its own epilogue warp: a query row is
+//        scanned by two threads - one for the even, one for the odd corpus tiles - each with its own threshold
+//        tau (a register) and its own candidate list (<= 512 packed (score, index) keys in an L2-resident
+//        scratch area).  A warp therefore has two tile periods for one tile, and the UMMAs of the next tile run
+//        while it reads.  Per 32-column chunk the thread reduces its 32 scores to four group maxima and compares
+//        once; a row with a candidate parks the chunk in its own shared-memory slot (no vote, no cross-lane
+//        traffic) and filters it after the accumulator has been handed back.  A full list is cut back to its
+//        best `kp` entries by a warp-wide bisection on the score bits (no sort in the scan).
 //        All CTAs walk the corpus from the same end at the same pace, so a corpus tile is fetched from
 //        HBM once per wave and served to the other SMs from L2.
-//   2. mips_finalize_kernel (one warp per query): merges the per-part candidate lists, re-scores the
+//        What was measured on the way (profiles/r02_summary.md): the 128 x 256 single-buffer layout of round 1
+//        was bound by the accumulator read phase (hit-free ceiling 1034 TFLOP/s) and a warp-cooperative hit
+//        queue (3.4 k cycles per tile); with double buffering the hit-free ceiling is 1390 TFLOP/s and the
+//        remaining cost is the serial latency of the rare-hit path of a warp (about 7 cycles per instruction
+//        with 5 warps per sub-partition), which is why it is lane-local, branch-light and off the read phase.
+//   2. mips_finalize_kernel (one warp per query): merges the sorted per-part candidate lists (bitonic merge), re-scores the
 //        best kp = k + margin candidates in fp32 against the fp32 corpus (the reference's arithmetic),
 //        sorts by (score desc, index asc) and writes the top k.
 // Ordering rule for exact ties: ascending corpus index (torch.topk leaves it unspecified).
+#include <cstdio>
+#include <vector>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,9 +40,23 @@ namespace {
 
 constexpr int LCAP = 512;   // candidate-list capacity per query row (keys)
 constexpr int KP_MAX = 256; // screening depth limit (k + margin)
+static_assert(LCAP == 2 * KP_MAX, "the finalize merge lays two KP_MAX-key runs side by side");
 constexpr int QT = 128;     // query rows per tile
-constexpr int CN = 256;     // corpus rows per tile (UMMA N)
-constexpr int QCAP = 32;    // parked rows per warp queue (32 x 128 B = the warp's 4 KB scratch; tags live beside it)
+constexpr int CN = 128;     // corpus rows per tile (UMMA N)
+constexpr int NBUF = 2;     // accumulator buffers per query tile; 2 query tiles x NBUF x CN = the 512 TMEM columns
+#ifndef TT_MIPS_CW
+#define TT_MIPS_CW 32
+#endif
+constexpr int CW = TT_MIPS_CW;  // score columns per TMEM load / compare / parking slot (16: next load in flight during the compare)
+static_assert(CW == 16 || CW == 32, "chunk width");
+#ifndef TT_MIPS_TRIG
+#define TT_MIPS_TRIG 128  // new keys between two threshold refreshes of a list (screen kernel 24.6 / 23.9 / 24.3 / 24.8 / 25.0 ms at 96 / 128 / 160 / 208 / 252)
+#endif
+#ifndef TT_MIPS_SLEEP
+#define TT_MIPS_SLEEP 0
+#endif
+constexpr int EPI_WARPS = 4 * 2 * NBUF;          // one warp per (query tile, accumulator buffer, TMEM lane quarter)
+constexpr int SCREEN_THREADS = 128 + 32 * EPI_WARPS;
 
 // ---- packed keys: (order-preserving score bits << 32) | ~index ; larger key = better candidate ----------
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -47,6 +71,46 @@ __device__ __forceinline__ unsigned long long make_key(float s, uint32_t idx) {
   return ((unsigned long long)f2ord(s) << 32) | (unsigned long long)(~idx);
 }
 __device__ __forceinline__ uint32_t key_idx(unsigned long long k) { return ~(uint32_t)k; }
+
+// explicit shared-window accesses (the parking slots are addressed by 32-bit shared addresses, not generic pointers)
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+  return r;
+}
+
+// barrier wait of the producer roles: a short sleep between probes leaves the issue slots of the sub-partition to the
+// epilogue warps that share it
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (TT_MIPS_SLEEP == 0) { mbar_wait(bar, parity); return; }
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait_addr(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(addr, parity)) {
+    __nanosleep(TT_MIPS_SLEEP);
+    if (clock64() - t0 > TT_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
+
+#ifdef TT_MIPS_BRINGUP  // clock stamps of one epilogue warp of CTA 0 (tools/mips_trace.py) and partial epilogues
+#define MIPS_STAMP(slot_, val_)                                                                         \
+  do {                                                                                                  \
+    if (a.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && u == 0)                      \
+      a.trace[(size_t)(j - j0) * 16 + (slot_)] = (val_);                                                \
+  } while (0)
+#define MIPS_DBG(bit_) (a.dbg & (bit_))
+#else
+#define MIPS_STAMP(slot_, val_) do { } while (0)
+#define MIPS_DBG(bit_) 0
+#endif
 
 // Bitonic sort (descending) of n keys (power of two, 64 <= n <= 512) held in shared memory, by one warp.
 __device__ void warp_sort_desc(unsigned long long* s, int n, int lane) {
@@ -67,6 +131,23 @@ __device__ void warp_sort_desc(unsigned long long* s, int n, int lane) {
   }
 }
 
+// Merge step of the bitonic network: n keys, first half descending and second half ascending (or any bitonic order)
+// -> all n descending.  log2(n) passes instead of the log2(n) (log2(n) + 1) / 2 of a full sort.
+__device__ void warp_bitonic_merge_desc(unsigned long long* s, int n, int lane) {
+  for (int j = n >> 1; j > 0; j >>= 1) {
+    for (int t = lane; t < (n >> 1); t += 32) {
+      const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const int hi = lo | j;
+      const unsigned long long a = s[lo], b = s[hi];
+      if (a < b) {
+        s[lo] = b;
+        s[hi] = a;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct ScreenArgs {
   int nq, nc, kp;
   int G;         // grid size
@@ -75,6 +156,10 @@ struct ScreenArgs {
   int CT;        // corpus tiles
   unsigned long long* lists;  // [G][2][128][LCAP] scratch
   unsigned long long* part;   // [slots][2][128][kp] per-unit results (best kp, unsorted beyond "top kp")
+#ifdef TT_MIPS_BRINGUP
+  int dbg;
+  long long* trace;  // [tile][16] clock stamps of one epilogue warp of CTA 0
+#endif
 };
 
 template <int DP>
@@ -82,9 +167,9 @@ struct ScreenCfg {
   static constexpr int KBOX = DP / 64;
   static constexpr int Q_BYTES = QT * DP * 2;   // one query tile
   static constexpr int C_BYTES = CN * DP * 2;   // one corpus stage
-  static constexpr int STAGES = DP == 64 ? 4 : 2;
-  static constexpr int SORT_BYTES = 8 * LCAP * 8;  // one 4 KB scratch per epilogue warp
-  static constexpr int TAG_BYTES = 8 * QCAP * 4;   // (chunk, row) tag per parked row and epilogue warp
+  static constexpr int STAGES = DP == 64 ? 4 : 3;
+  static constexpr int SORT_BYTES = EPI_WARPS * LCAP * 8;  // one 4 KB scratch per epilogue warp
+  static constexpr int TAG_BYTES = 0;
   static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * C_BYTES + SORT_BYTES + TAG_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -93,7 +178,7 @@ struct ScreenCfg {
 // the largest threshold t with count(score >= t) >= kp, keeps those keys (>= kp of them; more only on exact
 // score ties), returns the new count and threshold.  Warp-cooperative; falls back to an exact sort when ties
 // would leave the list too full.
-__device__ void warp_compact(unsigned long long* list, int n, int kp, float tau_in, unsigned long long* sscr, int lane,
+__device__ __noinline__ void warp_compact(unsigned long long* list, int n, int kp, float tau_in, unsigned long long* sscr, int lane,
                              int& n_out, float& tau_out) {
   unsigned long long k[LCAP / 32];
 #pragma unroll
@@ -146,7 +231,7 @@ __device__ void warp_compact(unsigned long long* list, int n, int kp, float tau_
 }
 
 template <int DP>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(SCREEN_THREADS, 1)
 mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmc, const ScreenArgs a) {
   using Cfg = ScreenCfg<DP>;
   extern __shared__ uint8_t smem_raw[];
@@ -154,13 +239,12 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   uint8_t* sq = smem;                                   // 2 query tiles
   uint8_t* sc = smem + 2 * Cfg::Q_BYTES;                // corpus ring
   unsigned long long* ssort = reinterpret_cast<unsigned long long*>(sc + Cfg::STAGES * Cfg::C_BYTES);
-  int* stags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES + Cfg::TAG_BYTES);
   uint64_t* q_full = bars;          // [1]
   uint64_t* q_empty = bars + 1;     // [1]
-  uint64_t* d_full = bars + 2;      // [2]
-  uint64_t* d_empty = bars + 4;     // [2]
-  uint64_t* c_full = bars + 6;      // [STAGES]
+  uint64_t* d_full = bars + 2;      // [2][NBUF]
+  uint64_t* d_empty = bars + 6;     // [2][NBUF]
+  uint64_t* c_full = bars + 10;     // [STAGES]
   uint64_t* c_empty = c_full + Cfg::STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c_empty + Cfg::STAGES);
 
@@ -172,7 +256,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 * NBUF; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 4);
     }
@@ -222,7 +306,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           for (int b = 0; b < Cfg::KBOX; ++b)
             tma_load_2d(sq + e * Cfg::Q_BYTES + b * (QT * 128), &tmq, q_full, b * 64, (qb * 2 + e) * QT);
         for (int j = j0; j < j1; ++j) {
-          mbar_wait(&c_empty[stage], phase ^ 1);
+          mbar_wait_relaxed(&c_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&c_full[stage], Cfg::C_BYTES);
           uint8_t* dst = sc + stage * Cfg::C_BYTES;
 #pragma unroll
@@ -247,14 +331,17 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
           mbar_wait(&c_full[stage], phase);
           const uint64_t dc = desc_advance(dc0, stage * Cfg::C_BYTES);
 #pragma unroll
+          const uint32_t buf = t % NBUF, use = t / NBUF;  // accumulator buffer of this tile and its use count
+#pragma unroll
           for (int e = 0; e < 2; ++e) {
-            mbar_wait(&d_empty[e], (t & 1) ^ 1);
+            mbar_wait_relaxed(&d_empty[e * NBUF + buf], (use & 1) ^ 1);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < DP / 16; ++k)
-              umma_bf16_w(tmem_base + e * CN, desc_advance(dq0, e * Cfg::Q_BYTES + (k >> 2) * (QT * 128) + (k & 3) * 32),
+              umma_bf16_w(tmem_base + (e * NBUF + buf) * CN,
+                          desc_advance(dq0, e * Cfg::Q_BYTES + (k >> 2) * (QT * 128) + (k & 3) * 32),
                           desc_advance(dc, (k >> 2) * (CN * 128) + (k & 3) * 32), idesc, k > 0 ? 1u : 0u, leader);
-            umma_commit_w(&d_full[e], leader);
+            umma_commit_w(&d_full[e * NBUF + buf], leader);
           }
           umma_commit_w(&c_empty[stage], leader);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -263,16 +350,19 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    const int e = (warp - 4) >> 2;  // epilogue group <-> query tile <-> accumulator
+    const int e = (warp - 4) >> 3;        // query tile of the CTA
+    const int par = ((warp - 4) >> 2) & 1;  // accumulator buffer = parity of the corpus tiles this warp scans
     const int q = warp & 3;         // TMEM lane quarter
     const int row = q * 32 + lane;  // row of the query tile owned by this thread
-    unsigned long long* sscr = ssort + (warp - 4) * LCAP;
-    float* fscr = reinterpret_cast<float*>(sscr);                 // parked rows: QCAP x 32 floats
-    int* qmeta = stags + (warp - 4) * QCAP;                       // (chunk << 5) | row tag per parked row
-    unsigned long long* sscr2 = sscr;  // exact-sort fallback of warp_compact: only entered with an empty queue (see drain)
-    // this warp's 32 lists: [cta][e][row][LCAP]
-    unsigned long long* wlists = a.lists + (((size_t)blockIdx.x * 2 + e) * QT + q * 32) * LCAP;
-    const int trig = (a.kp + 160 < LCAP - 64) ? a.kp + 160 : LCAP - 64;  // list length that triggers a threshold refresh
+    unsigned long long* sscr = ssort + (warp - 4) * LCAP;  // unit-end sort scratch of this warp
+    // this warp's 32 lists: [cta][e][row][LCAP]; a thread appends to the list of its own query row
+    unsigned long long* wlists = a.lists + ((((size_t)blockIdx.x * 2 + e) * NBUF + par) * QT + q * 32) * LCAP;
+    unsigned long long* mylist = wlists + (size_t)lane * LCAP;
+    const uint32_t park = smem_u32(sscr) + lane * (CW * 4);  // this row's parking slot in the warp's scratch
+    const int sw = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);  // 16-byte pieces of a slot are XOR-swizzled against bank conflicts
+    // list length that triggers a threshold refresh (checked once per tile); a tile adds at most CN keys to a list of
+    // fewer than max(trig, LCAP - 191) keys, which stays within LCAP
+    const int trig = (a.kp + TT_MIPS_TRIG < LCAP - CN) ? a.kp + TT_MIPS_TRIG : LCAP - CN;
     uint32_t t = 0;
     for (int u = 0; u < n_units; ++u) {
       int qb, j0, j1, slot;
@@ -280,90 +370,132 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       float tau = -INFINITY;
       int cnt = 0;
       for (int j = j0; j < j1; ++j, ++t) {
-        mbar_wait(&d_full[e], t & 1);
+        const uint32_t buf = t % NBUF, use = t / NBUF;
+        if ((int)buf != par) continue;  // the tiles of the other buffer belong to the sibling warp (own lists, own threshold)
+        MIPS_STAMP(0, clock64());
+        mbar_wait_relaxed(&d_full[e * NBUF + buf], use & 1);
         tc_fence_after();
-        // Pass 1 (holds the accumulator): per 32-column chunk a max tree and one compare per row; rows with a
-        // candidate are PARKED (their 32 scores + (row, chunk) tag) in the warp's shared-memory queue.
-        // Pass 2 (after the accumulator has been handed back, i.e. off the UMMA critical path): the parked rows
-        // are filtered against their thresholds and appended to the candidate lists.
-        int nq_ = 0;  // parked rows in the queue (warp-uniform)
-        auto drain = [&]() {
-          const uint32_t below = (1u << lane) - 1u;
-          for (int s0 = 0; s0 < nq_; s0 += 2) {  // two rows per step: their load / ballot chains overlap
-            const int s1 = s0 + 1 < nq_ ? s0 + 1 : s0;
-            const bool two = s1 != s0;
-            const int tag0 = qmeta[s0], tag1 = qmeta[s1];
-            const int r0 = tag0 & 31, r1 = tag1 & 31;
-            const float x0 = fscr[s0 * 32 + lane], x1 = fscr[s1 * 32 + lane];
-            const float t0 = __shfl_sync(0xffffffffu, tau, r0), t1 = __shfl_sync(0xffffffffu, tau, r1);
-            const int c0 = __shfl_sync(0xffffffffu, cnt, r0);
-            const int col0 = j * CN + (tag0 >> 5) * 32 + lane, col1 = j * CN + (tag1 >> 5) * 32 + lane;
-            const bool p0 = (x0 > t0) && (col0 < a.nc);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, p0);
-            if (p0) wlists[(size_t)r0 * LCAP + c0 + __popc(b0 & below)] = make_key(x0, (uint32_t)col0);
-            if (lane == r0) cnt = c0 + __popc(b0);
-            // the second row may be the same query row (another chunk of it): read its count after the update
-            const int c1 = __shfl_sync(0xffffffffu, cnt, r1);
-            const bool p1 = two && (x1 > t1) && (col1 < a.nc);
-            const uint32_t b1 = __ballot_sync(0xffffffffu, p1);
-            if (p1) wlists[(size_t)r1 * LCAP + c1 + __popc(b1 & below)] = make_key(x1, (uint32_t)col1);
-            if (two && lane == r1) cnt = c1 + __popc(b1);
-            // lists close to their capacity are cut back to their best entries (threshold refresh); rare
-            uint32_t full = __ballot_sync(0xffffffffu, cnt >= trig);
-            while (full) {
-              const int r = __ffs(full) - 1;
-              full &= full - 1;
-              int cnt_r = __shfl_sync(0xffffffffu, cnt, r);
-              float new_tau = __shfl_sync(0xffffffffu, tau, r);
-              warp_compact(wlists + (size_t)r * LCAP, cnt_r, a.kp, new_tau, sscr2, lane, cnt_r, new_tau);
-              if (lane == r) { cnt = cnt_r; tau = new_tau; }
+        MIPS_STAMP(1, clock64());
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (e * NBUF + buf) * CN;
+        const bool ragged = (j + 1) * CN > a.nc;  // last corpus tile: columns past the corpus end score 0 (TMA zero fill)
+        // Read phase (holds the accumulator buffer): CW-column chunks of the thread's query row are reduced to the maxima
+        // of their 8-column groups and compared against the row's threshold (CW = 16: with the TMEM load of the next
+        // chunk in flight).  A row with a candidate PARKS the chunk in its own slot of the warp's scratch (no vote,
+        // no cross-lane traffic).  Filtering a parked chunk is lane-local too: it happens when the row needs its
+        // slot again within the tile (rare outside the first tiles) or, normally, after the buffer has been handed
+        // back.
+        constexpr int NG = CW / 8;  // groups per chunk
+        unsigned long long* dst = mylist + cnt;
+        int pend = -1;      // parked chunk of this row (-1: none)
+        uint32_t pgrp = 0;  // its groups that beat the threshold
+        auto drain_own = [&]() {
+          // usually one group with one score above the threshold: a bit mask of the group's eight compares, then the
+          // survivors are re-read from the slot by index
+          const uint32_t col0 = (uint32_t)(j * CN + pend * CW);
+          while (pgrp) {
+            const int k = __ffs(pgrp) - 1;
+            pgrp &= pgrp - 1;
+            const float4 x0 = lds128(park + (((2 * k) ^ sw) << 4)), x1 = lds128(park + (((2 * k + 1) ^ sw) << 4));
+            uint32_t m = (x0.x > tau ? 1u : 0u) | (x0.y > tau ? 2u : 0u) | (x0.z > tau ? 4u : 0u) | (x0.w > tau ? 8u : 0u) |
+                         (x1.x > tau ? 16u : 0u) | (x1.y > tau ? 32u : 0u) | (x1.z > tau ? 64u : 0u) | (x1.w > tau ? 128u : 0u);
+            while (m) {
+              const int i = __ffs(m) - 1;
+              m &= m - 1;
+              *dst++ = make_key(lds32(park + ((((2 * k + (i >> 2)) ^ sw) << 4) | ((i & 3) << 2))), col0 + 8 * k + i);
             }
           }
-          __syncwarp();
-          nq_ = 0;
         };
+        auto scan = [&](float* v, int c) {
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i)
+              if (j * CN + c * CW + i >= a.nc) v[i] = -INFINITY;
+          }
+          float g[NG];
+#pragma unroll
+          for (int k = 0; k < NG; ++k) {  // three 3-input maxima and one 2-input per group
+            const float m0 = fmaxf(fmaxf(v[8 * k], v[8 * k + 1]), v[8 * k + 2]);
+            const float m1 = fmaxf(fmaxf(v[8 * k + 3], v[8 * k + 4]), v[8 * k + 5]);
+            g[k] = fmaxf(fmaxf(fmaxf(m0, m1), v[8 * k + 6]), v[8 * k + 7]);
+          }
+          float gm = fmaxf(g[0], g[1]);
+          if (NG == 4) gm = fmaxf(fmaxf(gm, g[2]), g[3]);
+          if (gm > tau && !MIPS_DBG(1)) {
+            if (pend >= 0) drain_own();
+            pend = c;
+            pgrp = 0;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) pgrp |= g[k] > tau ? (1u << k) : 0u;
+#pragma unroll
+            for (int i = 0; i < CW / 4; ++i) sts128(park + ((i ^ sw) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        };
+        if constexpr (CW == 16) {
+          float va[16], vb[16];
+          tmem_ld16(tcol, va);
 #pragma unroll 1
-        for (int c = 0; c < CN / 32; ++c) {
+          for (int c = 0; c < CN / 16; c += 2) {
+            tmem_wait_ld();
+            tmem_ld16(tcol + (c + 1) * 16, vb);
+            MIPS_STAMP(4 + c, clock64());
+            if (!MIPS_DBG(2)) scan(va, c);
+            tmem_wait_ld();
+            if (c + 2 < CN / 16) {
+              tmem_ld16(tcol + (c + 2) * 16, va);
+            } else {  // accumulator fully read: hand it back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&d_empty[e * NBUF + buf]);
+            }
+            MIPS_STAMP(5 + c, clock64());
+            if (!MIPS_DBG(2)) scan(vb, c + 1);
+          }
+        } else {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + e * CN + c * 32, v);
-          tmem_wait_ld();
-          if (c == CN / 32 - 1) {  // accumulator fully read: hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[e]);
+#pragma unroll 1
+          for (int c = 0; c < CN / 32; ++c) {
+            tmem_ld32(tcol + c * 32, v);
+            tmem_wait_ld();
+            MIPS_STAMP(4 + 2 * c, clock64());
+            if (c == CN / 32 - 1) {  // accumulator fully read: hand it back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&d_empty[e * NBUF + buf]);
+            }
+            if (!MIPS_DBG(2)) scan(v, c);
           }
-          float m0 = fmaxf(fmaxf(v[0], v[1]), v[2]), m1 = fmaxf(fmaxf(v[3], v[4]), v[5]);
-          float m2 = fmaxf(fmaxf(v[6], v[7]), v[8]), m3 = fmaxf(fmaxf(v[9], v[10]), v[11]);
-#pragma unroll
-          for (int i = 12; i < 32; i += 4) {
-            m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
-          }
-          const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          const bool hit = m > tau;
-          const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-          if (hits == 0) continue;
-          const int nh = __popc(hits);
-          if (nq_ + nh > QCAP) drain();  // queue full (early in a scan): filter what is parked first
-          if (hit) {
-            const int s_ = nq_ + __popc(hits & ((1u << lane) - 1u));
-            qmeta[s_] = (c << 5) | lane;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(fscr + s_ * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          nq_ += nh;
-          __syncwarp();
         }
-        if (nq_ > 0) drain();
+        MIPS_STAMP(2, clock64());
+        if (__any_sync(0xffffffffu, pend >= 0)) {
+          if (pend >= 0) drain_own();
+          cnt = (int)(dst - mylist);
+          MIPS_STAMP(12, clock64());
+          // lists close to their capacity are cut back to their best entries (threshold refresh); rare
+          uint32_t full = __ballot_sync(0xffffffffu, cnt >= trig);
+          MIPS_STAMP(13, clock64());
+          MIPS_STAMP(14, full);
+          while (full) {
+            const int rr = __ffs(full) - 1;
+            full &= full - 1;
+            __syncwarp();  // the owner's appends are visible to the whole warp
+            int cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
+            float new_tau = __shfl_sync(0xffffffffu, tau, rr);
+            warp_compact(wlists + (size_t)rr * LCAP, cnt_r, a.kp, new_tau, sscr, lane, cnt_r, new_tau);
+            if (lane == rr) { cnt = cnt_r; tau = new_tau; }
+          }
+        }
+        MIPS_STAMP(3, clock64());
       }
+      __syncwarp();
       // unit done: exact order of each row's list, best kp keys -> part[slot][e][row][kp]
       for (int r = 0; r < 32; ++r) {
         const int n = __shfl_sync(0xffffffffu, cnt, r);
         const unsigned long long* list = wlists + (size_t)r * LCAP;
-        for (int i = lane; i < LCAP; i += 32) sscr[i] = i < n ? list[i] : 0ull;
+        const int ns = n <= LCAP / 2 ? LCAP / 2 : LCAP;  // kp <= LCAP / 2
+        for (int i = lane; i < ns; i += 32) sscr[i] = i < n ? list[i] : 0ull;
         __syncwarp();
-        warp_sort_desc(sscr, LCAP, lane);
-        unsigned long long* dst = a.part + (((size_t)slot * 2 + e) * QT + q * 32 + r) * a.kp;
+        warp_sort_desc(sscr, ns, lane);
+        unsigned long long* dst = a.part + ((((size_t)slot * 2 + e) * NBUF + par) * QT + q * 32 + r) * a.kp;
         for (int i = lane; i < a.kp; i += 32) dst[i] = sscr[i];
         __syncwarp();
       }
@@ -403,16 +535,18 @@ __global__ void __launch_bounds__(128) mips_finalize_kernel(const FinalArgs a) {
   int slot0, nparts;
   if (qb < a.R * a.G) { slot0 = qb; nparts = 1; }
   else { slot0 = a.R * a.G + (qb - a.R * a.G) * a.S; nparts = a.S; }
-  // merged best kp by screening score
-  for (int i = lane; i < LCAP; i += 32) s[i] = 0ull;
-  __syncwarp();
-  for (int p = 0; p < nparts; ++p) {
-    const unsigned long long* src = a.part + (((size_t)(slot0 + p) * 2 + e) * QT + rr) * a.kp;
-    // s[0, kp) holds the running best (sorted); append the next part behind it and re-sort
-    for (int i = lane; i < a.kp; i += 32) s[KP_MAX + i] = src[i];
-    for (int i = a.kp + lane; i < KP_MAX; i += 32) { s[i] = 0ull; s[KP_MAX + i] = 0ull; }
+  // merged best kp by screening score: every part is sorted (descending, zero padded).  The running best lives in
+  // s[0, KP_MAX); the next part is laid behind it in REVERSE order, which makes the 2 KP_MAX keys a bitonic sequence,
+  // and one merge pass set sorts them.
+  for (int p = 0; p < nparts * NBUF; ++p) {
+    const unsigned long long* src = a.part + ((((size_t)(slot0 + p / NBUF) * 2 + e) * NBUF + p % NBUF) * QT + rr) * a.kp;
+    if (p == 0) {
+      for (int i = lane; i < KP_MAX; i += 32) s[i] = i < a.kp ? src[i] : 0ull;
+    } else {
+      for (int i = lane; i < KP_MAX; i += 32) s[LCAP - 1 - i] = i < a.kp ? src[i] : 0ull;
+    }
     __syncwarp();
-    if (nparts > 1 || p == 0) warp_sort_desc(s, LCAP, lane);
+    if (p > 0) warp_bitonic_merge_desc(s, LCAP, lane);
   }
   // fp32 re-score of the kp candidates (the reference scores in fp32: src/baseline_mips_module.py:58)
   const float* qrow = a.q32 + row * a.ldq;
@@ -479,7 +613,7 @@ static int make_plan(long long nq, long long nc, long long d, long long k, Plan&
 size_t mips_workspace_bytes(long long Q, long long C, long long d, long long k) {
   Plan p;
   make_plan(Q, C, d, k, p);
-  return (size_t)p.G * 2 * QT * LCAP * 8 + (size_t)p.slots * 2 * QT * p.kp * 8 + 1024;
+  return (size_t)p.G * 2 * NBUF * QT * LCAP * 8 + (size_t)p.slots * 2 * NBUF * QT * p.kp * 8 + 1024;
 }
 
 template <int DP>
@@ -491,7 +625,7 @@ static int launch_screen(const CUtensorMap& tq, const CUtensorMap& tc, const Scr
     configured = true;
   }
   KernelSpan span("mips_screen_kernel", st);
-  mips_screen_kernel<DP><<<a.G, 384, Cfg::SMEM_BYTES, st>>>(tq, tc, a);
+  mips_screen_kernel<DP><<<a.G, SCREEN_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tc, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -514,7 +648,17 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
   a.nq = (int)nq; a.nc = (int)nc; a.kp = p.kp;
   a.G = p.G; a.R = p.R; a.r = p.r; a.S = p.S; a.CT = p.CT;
   a.lists = (unsigned long long*)ws;
-  a.part = a.lists + (size_t)p.G * 2 * QT * LCAP;
+#ifdef TT_MIPS_BRINGUP
+  a.dbg = getenv("TT_MIPS_DBG") ? atoi(getenv("TT_MIPS_DBG")) : 0;
+  a.trace = nullptr;
+  static long long* trace_dev = nullptr;
+  if (getenv("TT_MIPS_TRACE")) {
+    if (!trace_dev) cudaMalloc(&trace_dev, (size_t)p.CT * 16 * 8);
+    cudaMemset(trace_dev, 0, (size_t)p.CT * 16 * 8);
+    a.trace = trace_dev;
+  }
+#endif
+  a.part = a.lists + (size_t)p.G * 2 * NBUF * QT * LCAP;
   CUtensorMap tq, tc;
   int rc = make_tmap_bf16(&tq, Q16, d, nq, ldq, 64, QT);
   if (rc) return rc;
@@ -530,6 +674,15 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
   f.idx_out = idx; f.score_out = scores;
   KernelSpan span("mips_finalize_kernel", stream);
   mips_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(f);
+#ifdef TT_MIPS_BRINGUP
+  if (a.trace) {
+    cudaStreamSynchronize(stream);
+    std::vector<long long> h((size_t)p.CT * 16);
+    cudaMemcpy(h.data(), a.trace, h.size() * 8, cudaMemcpyDeviceToHost);
+    FILE* fp = fopen(getenv("TT_MIPS_TRACE"), "wb");
+    if (fp) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+  }
+#endif
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
