@@ -625,7 +625,7 @@ def run_base(args, rank, world, local_rank, d, light):
     N = B * world
     kern = {}
     alg = {k_: 2.0 * B * N * d for k_ in ("ce_fwd_kernel", "ce_bwd2_kernel_dU", "ce_bwd2_kernel_dV", "ce_bwd3_kernel_dU",
-                                           "ce_bwd3_kernel_dV")}
+                                           "ce_bwd3_kernel_dV", "ce_bwd3x_kernel_dU", "ce_bwd3x_kernel_dV")}
     for name, (tot, cnt) in spans.items():
         per = tot / max(cnt, 1)
         kern[name] = {"ms": per, "launches_per_step": cnt / n_prof}

@@ -124,3 +124,27 @@ def test_mips_full_size_properties():
     sub = torch.arange(0, nq, 64)
     ridx, rsc = oracle.mips_topk(q[sub], c, k)
     assert torch.equal(sc[sub], rsc) and torch.equal(idx[sub], ridx)
+
+
+def test_mips_config4_all_queries_sampled_oracle():
+    """BASELINE config 4 at its full size (65 536 queries x 1M corpus, d = 128, top-100) - the launch shape with one
+    full round of query blocks plus a tail whose corpus is cut into parts and merged by the finalize kernel.  Every
+    64th query is compared with the oracle: bit-exact indices and scores on exact-grid data (ties broken by index)."""
+    g = torch.Generator().manual_seed(21)
+    nq, nc, d, k = 65536, 1_000_000, 128, 100
+    q, c = _grid((nq, d), g), _grid((nc, d), g)
+    import two_tower_models_b200 as tt
+
+    m = tt.BaselineMIPSModule(corpus_size=nc, embedding_dim=d)
+    m.corpus = c.clone()
+    m = m.cuda()
+    idx, sc, emb = m(q.cuda(), k)
+    del emb  # [65536, 100, 128] fp32: not needed on the host
+    idx, sc = idx.cpu(), sc.cpu()
+    assert idx.shape == (nq, k) and int(idx.min()) >= 0 and int(idx.max()) < nc
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+    sub = torch.arange(0, nq, 64)
+    for lo in range(0, len(sub), 256):  # 256 oracle queries at a time: 1 GB of fp32 scores on the host
+        s = sub[lo:lo + 256]
+        ridx, rsc = oracle.mips_topk(q[s], c, k)
+        assert torch.equal(sc[s], rsc) and torch.equal(idx[s], ridx), lo

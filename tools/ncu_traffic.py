@@ -13,6 +13,7 @@ for r in rows[2:]:
     key = None
     for k, pat in [("ce_fwd_kernel", "ce_fwd_kernel"), ("ce_bwd2_kernel_dV", "ce_bwd2_kernel<128, 1>"), ("ce_bwd2_kernel_dU", "ce_bwd2_kernel<128, 0>"),
                    ("ce_bwd3_kernel_dU", "ce_bwd3_kernel<128, 1>"), ("ce_bwd3_kernel_dV", "ce_bwd3_kernel<128, 0>"),
+                   ("ce_bwd3x_kernel_dU", "ce_bwd3x_kernel<256, 1>"), ("ce_bwd3x_kernel_dV", "ce_bwd3x_kernel<256, 0>"),
                    ("tower_fwd_kernel", "tower_fwd_kernel"), ("ce_bwd_reduce_kernel", "ce_bwd_reduce_kernel"),
                    ("ce_combine_loss_kernel", "ce_combine_loss_kernel"), ("adam_kernel", "adam_kernel")]:
         if pat in name:

@@ -379,71 +379,92 @@ struct DiagOperands {
   long long rows_per_part, ldv, target_offset;
   int d;
 };
-// Block-cooperative version for 256-thread blocks with one row per thread: every warp computes the logits of its 32
-// rows with 16 (d <= 128) or 32 lanes per row, so the 16-byte loads of a row are coalesced and all of a lane's loads
-// are in flight together (one thread walking its own row pays one L2 round trip per 16 bytes).  Returns the logit of
-// the calling thread's row (row0 + threadIdx.x).
 static constexpr int COMBINE_RB = 64;  // rows per 256-thread block of the merge kernels
-// RB = rows per 256-thread block (the first RB threads own one row each afterwards).
-template <int RB>
-__device__ __forceinline__ float positive_logit_block(const DiagOperands& o, long long row0, int B, float* sdiag) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunks = (o.d + 7) / 8;            // 16-byte chunks per row (<= 32)
-  const int lpr = chunks <= 16 ? 16 : 32;      // lanes per row
-  const int rpi = 32 / lpr;                    // rows per warp iteration
-  const int sub = lane / lpr, c = lane % lpr;
-  constexpr int RW = RB / 8;                   // rows per warp
+// Quad layout of the merge kernels: 256-thread blocks own COMBINE_RB = 64 rows, thread (row, e) = (tid >> 2, tid & 3).
+// All loads of a thread are issued before the first use (the merge is a chain of L2 round trips otherwise).
+// Positive logit of `row`: the quad splits the row's 16-byte chunks; valid in all four lanes afterwards.
+__device__ __forceinline__ float positive_logit_quad(const DiagOperands& o, long long row, int B, int e) {
+  const int chunks = (o.d + 7) / 8;  // <= 32
+  uint4 a4[8], b4[8];
+  const bool live = row < B;
+  const long long t = row + o.target_offset;
+  const long long p = live ? t / o.rows_per_part : 0;
+  const bf16* urow = o.U + row * o.ldu;
+  const bf16* vrow = o.Vp[p] + (t - p * o.rows_per_part) * o.ldv;
 #pragma unroll
-  for (int i = 0; i < RW; ++i) {
-    if (i * rpi >= RW) break;
-    const int lr = warp * RW + i * rpi + sub;  // row inside the block
-    const long long row = row0 + lr;
-    float acc = 0.f;
-    if (row < B && c < chunks) {
-      const long long t = row + o.target_offset;
-      const long long p = t / o.rows_per_part;
-      const uint4 a4 = *reinterpret_cast<const uint4*>(o.U + row * o.ldu + c * 8);
-      const uint4 b4 = *reinterpret_cast<const uint4*>(o.Vp[p] + (t - p * o.rows_per_part) * o.ldv + c * 8);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
-      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = __bfloat1622float2(a2[k]), fb = __bfloat1622float2(b2[k]);
-        if (c * 8 + 2 * k < o.d) acc = fmaf(fa.x, fb.x, acc);
-        if (c * 8 + 2 * k + 1 < o.d) acc = fmaf(fa.y, fb.y, acc);
-      }
-    }
-    for (int off = lpr / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (c == 0) sdiag[lr] = acc;
+  for (int i = 0; i < 8; ++i) {
+    const int c = e + 4 * i;
+    const bool ok = live && c < chunks;
+    a4[i] = ok ? *reinterpret_cast<const uint4*>(urow + c * 8) : make_uint4(0, 0, 0, 0);
+    b4[i] = ok ? *reinterpret_cast<const uint4*>(vrow + c * 8) : make_uint4(0, 0, 0, 0);
   }
-  __syncthreads();
-  return sdiag[threadIdx.x % RB];
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = e + 4 * i;
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4[i]);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4[i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(a2[k]), fb = __bfloat1622float2(b2[k]);
+      if (c * 8 + 2 * k < o.d) acc = fmaf(fa.x, fb.x, acc);
+      if (c * 8 + 2 * k + 1 < o.d) acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  return acc;
+}
+// log-sum-exp (natural log) of `row` from the forward kernel's (max, sum-exp) partials in base 2: lane e of the quad
+// merges epilogue group e of every slot (four slots per batch of loads), then the quad folds.  Valid in all four lanes.
+__device__ __forceinline__ float merge_lse_quad(long long row, int B, long long Bpad, long long T, int CT,
+                                                const float* __restrict__ part_m, const float* __restrict__ part_s, int e) {
+  static_assert(FWD_EG == 4, "one quad lane per epilogue group");
+  const bool live = row < B;
+  const long long r = row / 128;
+  const int first = (int)((r * CT) / T), nsl = live ? (int)(((r + 1) * CT - 1) / T) - first + 1 : 0;
+  float M = -INFINITY, S = 0.f;
+  for (int s0 = 0; s0 < nsl; s0 += 4) {
+    float m[4], sm[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = s0 + u < nsl;
+      const long long o = (long long)((s0 + u) * FWD_EG + e) * Bpad + row;
+      m[u] = ok ? part_m[o] : -INFINITY;
+      sm[u] = ok ? part_s[o] : 0.f;
+    }
+    // an epilogue group without valid columns reports (-inf, 0): the clamp keeps -inf - -inf out of the exponent
+    const float mx = fmaxf(fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), M), -3.0e38f);
+    S *= exp2f(M - mx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) S += sm[u] * exp2f(m[u] - mx);
+    M = mx;
+  }
+#pragma unroll
+  for (int off = 1; off <= 2; off <<= 1) {
+    const float Mo = __shfl_xor_sync(0xffffffffu, M, off), So = __shfl_xor_sync(0xffffffffu, S, off);
+    const float mx = fmaxf(fmaxf(M, Mo), -3.0e38f);
+    S = (live ? S * exp2f(M - mx) + So * exp2f(Mo - mx) : 0.f);
+    M = mx;
+  }
+  return live ? (M + log2f(S)) * LN2 : 0.f;
 }
 
-__global__ void ce_combine_kernel(int B, long long Bpad, long long T, int CT, const float* part_m, const float* part_s,
-                                  const DiagOperands dg, float* ce, float* lse) {
-  __shared__ float sdiag[COMBINE_RB];
-  const long long row = (long long)blockIdx.x * COMBINE_RB + threadIdx.x;
-  const float pos = positive_logit_block<COMBINE_RB>(dg, (long long)blockIdx.x * COMBINE_RB, B, sdiag);
-  if (threadIdx.x >= COMBINE_RB || row >= B) return;
-  const long long r = row / 128;
-  const int first = (int)((r * CT) / T), last = (int)(((r + 1) * CT - 1) / T);
-  float M = -INFINITY;
-  for (int sl = 0; sl <= last - first; ++sl)
-    for (int e = 0; e < FWD_EG; ++e) M = fmaxf(M, part_m[(long long)(sl * FWD_EG + e) * Bpad + row]);
-  float S = 0.f;
-  for (int sl = 0; sl <= last - first; ++sl)
-    for (int e = 0; e < FWD_EG; ++e) {
-      const long long o = (long long)(sl * FWD_EG + e) * Bpad + row;
-      S += part_s[o] * exp2f(part_m[o] - M);
-    }
-  const float l = (M + log2f(S)) * LN2;
-  lse[row] = l;
-  ce[row] = l - pos;
+__global__ void __launch_bounds__(256)
+ce_combine_kernel(int B, long long Bpad, long long T, int CT, const float* part_m, const float* part_s,
+                  const DiagOperands dg, float* ce, float* lse) {
+  const int e = threadIdx.x & 3;
+  const long long row = (long long)blockIdx.x * COMBINE_RB + (threadIdx.x >> 2);
+  const float pos = positive_logit_quad(dg, row, B, e);
+  const float l = merge_lse_quad(row, B, Bpad, T, CT, part_m, part_s, e);
+  if (e == 0 && row < B) {
+    lse[row] = l;
+    ce[row] = l - pos;
+  }
 }
 
 // combine + value-weighted mean in ONE launch (identity debias hook, reference :322-343).  Every block merges the
-// (max, sum-exp) partials of 256 rows into ce / lse, forms nuv = max(labels . w, 1e-6) and reduces (max nuv,
+// (max, sum-exp) partials of 64 rows into ce / lse, forms nuv = max(labels . w, 1e-6) and reduces (max nuv,
 // sum ce nuv) over its rows; the last block to finish (atomic ticket) folds the per-block pairs in block order
 // (deterministic) into  loss = sum / (max B)  and  g_norm = 1 / (max B).  The backward kernels take g = nuv and
 // the device scalar g_norm, so the normalised weights never make a separate pass.
@@ -461,25 +482,13 @@ ce_combine_loss_kernel(int B, long long Bpad, long long T, int CT, const float* 
                        const float* __restrict__ uvw, int TL, float inv_rows, float* __restrict__ loss,
                        float* __restrict__ g, float* __restrict__ g_norm, LossSync* sync, float* __restrict__ stats) {
   __shared__ float red_m[8], red_s[8];
-  __shared__ float sdiag[COMBINE_RB];
   __shared__ unsigned int last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row = (long long)blockIdx.x * COMBINE_RB + tid;
-  const float pos = positive_logit_block<COMBINE_RB>(dg, (long long)blockIdx.x * COMBINE_RB, B, sdiag);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = tid & 3;
+  const long long row = (long long)blockIdx.x * COMBINE_RB + (tid >> 2);
+  const float pos = positive_logit_quad(dg, row, B, e);
+  const float l = merge_lse_quad(row, B, Bpad, T, CT, part_m, part_s, e);
   float nuv = 0.f, cw = 0.f;
-  if (tid < COMBINE_RB && row < B) {
-    const long long r = row / 128;
-    const int first = (int)((r * CT) / T), last_slot = (int)(((r + 1) * CT - 1) / T);
-    float M = -INFINITY;
-    for (int sl = 0; sl <= last_slot - first; ++sl)
-      for (int e = 0; e < FWD_EG; ++e) M = fmaxf(M, part_m[(long long)(sl * FWD_EG + e) * Bpad + row]);
-    float S = 0.f;
-    for (int sl = 0; sl <= last_slot - first; ++sl)
-      for (int e = 0; e < FWD_EG; ++e) {
-        const long long o = (long long)(sl * FWD_EG + e) * Bpad + row;
-        S += part_s[o] * exp2f(part_m[o] - M);
-      }
-    const float l = (M + log2f(S)) * LN2;
+  if (e == 0 && row < B) {
     const float c = l - pos;
     lse[row] = l;
     ce[row] = c;
