@@ -40,6 +40,13 @@ long long tt_launch_count(void);
  * synchronises the device and writes one line per kernel name, "name total_ms launches\n", into buf. */
 void tt_profile_enable(int on);
 int tt_profile_report(char* buf, int64_t buf_bytes);
+/* on = 2 also brackets launches made under stream capture (external event-record nodes in the CUDA graph): every
+ * replay of such a graph re-stamps its events, and tt_profile_report_graph reports the spans of the LAST replay
+ * (same line format; clear != 0 forgets the captured spans - call it before the graph is destroyed). */
+int tt_profile_report_graph(char* buf, int64_t buf_bytes, int32_t clear);
+/* Launches an EMPTY kernel inside a span named "null_kernel": its reported time is what an event pair adds to every
+ * span taken the same way (eager or inside a graph), i.e. the calibration of the per-kernel numbers. */
+int tt_profile_null_span(void* stream);
 
 /* ---- data movement (HBM-bound helpers) ------------------------------------------------------ */
 

@@ -86,6 +86,8 @@ SIGNATURES = {
     "tt_launch_count": (I64, []),
     "tt_profile_enable": (None, [I32]),
     "tt_profile_report": (I32, [P, I64]),
+    "tt_profile_report_graph": (I32, [P, I64, I32]),
+    "tt_profile_null_span": (I32, [P]),
     "tt_cast_rows_bf16": (I32, [P, I64, I64, I64, P, I64, I64, P]),
     "tt_gather_rows_bf16": (I32, [P, I64, I64, P, I64, P, I64, P, P]),
     "tt_gather_rows_f32": (I32, [P, I64, I64, P, I64, P, I64, P, P]),

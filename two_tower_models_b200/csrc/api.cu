@@ -30,26 +30,32 @@ struct SpanRec {
   const char* name;
   cudaEvent_t e0, e1;
 };
-static std::atomic<int> g_profile{0};
+static std::atomic<int> g_profile{0};  // 1: eager launches; 2: launches under stream capture too (external event nodes)
 static std::mutex g_span_mu;
-static std::vector<SpanRec> g_spans;
+static std::vector<SpanRec> g_spans;        // eager launches since the last report
+static std::vector<SpanRec> g_graph_spans;  // launches captured into CUDA graphs: re-stamped by every replay
 
-KernelSpan::KernelSpan(const char* name, cudaStream_t stream) : rec_(nullptr), stream_(stream) {
-  if (!g_profile.load(std::memory_order_relaxed)) return;
+KernelSpan::KernelSpan(const char* name, cudaStream_t stream) : rec_(nullptr), stream_(stream), captured_(false) {
+  const int mode = g_profile.load(std::memory_order_relaxed);
+  if (!mode) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) return;
+  captured_ = cs != cudaStreamCaptureStatusNone;
+  if (captured_ && mode < 2) return;
   SpanRec* r = new SpanRec{name, nullptr, nullptr};
   cudaEventCreate(&r->e0);
   cudaEventCreate(&r->e1);
-  cudaEventRecord(r->e0, stream);
+  if (captured_) cudaEventRecordWithFlags(r->e0, stream, cudaEventRecordExternal);
+  else cudaEventRecord(r->e0, stream);
   rec_ = r;
 }
 KernelSpan::~KernelSpan() {
   if (!rec_) return;
   SpanRec* r = static_cast<SpanRec*>(rec_);
-  cudaEventRecord(r->e1, stream_);
+  if (captured_) cudaEventRecordWithFlags(r->e1, stream_, cudaEventRecordExternal);
+  else cudaEventRecord(r->e1, stream_);
   std::lock_guard<std::mutex> lk(g_span_mu);
-  g_spans.push_back(*r);
+  (captured_ ? g_graph_spans : g_spans).push_back(*r);
   delete r;
 }
 
@@ -111,7 +117,7 @@ const char* tt_last_error(void) { return g_err; }
 
 long long tt_launch_count(void) { return (long long)g_launches.load(); }
 
-void tt_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+void tt_profile_enable(int on) { g_profile.store(on < 0 ? 0 : (on > 2 ? 2 : on)); }
 
 int tt_profile_report(char* buf, int64_t buf_bytes) {
   TT_CUDA(cudaDeviceSynchronize());
@@ -138,6 +144,45 @@ int tt_profile_report(char* buf, int64_t buf_bytes) {
   }
   TT_CHECK((int64_t)out.size() + 1 <= buf_bytes, "tt_profile_report: buffer too small");
   memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+int tt_profile_report_graph(char* buf, int64_t buf_bytes, int32_t clear) {
+  TT_CUDA(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<double, long long>> agg;
+  {
+    std::lock_guard<std::mutex> lk(g_span_mu);
+    for (auto& r : g_graph_spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        auto& a = agg[r.name];
+        a.first += ms;
+        a.second += 1;
+      }
+      if (clear) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+      }
+    }
+    if (clear) g_graph_spans.clear();
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  TT_CHECK((int64_t)out.size() + 1 <= buf_bytes, "tt_profile_report_graph: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+// An empty kernel inside a span: what the event pair itself adds to every kernel span measured the same way.
+__global__ void null_kernel() {}
+int tt_profile_null_span(void* stream) {
+  KernelSpan span("null_kernel", (cudaStream_t)stream);
+  null_kernel<<<1, 32, 0, (cudaStream_t)stream>>>();
+  TT_CUDA(cudaGetLastError());
   return 0;
 }
 

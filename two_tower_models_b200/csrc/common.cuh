@@ -40,6 +40,7 @@ struct KernelSpan {
   ~KernelSpan();
   void* rec_;
   cudaStream_t stream_;
+  bool captured_;
 };
 // Encode a 2-D bf16 tensor map: tensor [outer, inner] with row pitch `pitch_elems` (elements),
 // box [box_outer, box_inner], 128-byte swizzle, zero fill out of bounds.

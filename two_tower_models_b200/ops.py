@@ -62,9 +62,28 @@ class _span:
         return False
 
 
-def profile_kernels(on: bool) -> None:
-    """Bracket every kernel the library launches (outside stream capture) with CUDA events."""
-    _native.lib().tt_profile_enable(1 if on else 0)
+def profile_kernels(on) -> None:
+    """Bracket every kernel the library launches with CUDA events: True / 1 = eager launches only, 2 = launches under
+    stream capture too (external event nodes; read them with profile_graph_report after a replay)."""
+    _native.lib().tt_profile_enable(int(on))
+
+
+def profile_null_span() -> None:
+    """An empty kernel inside a span ("null_kernel" in the reports): the overhead of the event pair of a span."""
+    _native.check(_native.lib().tt_profile_null_span(_stream()), "profile_null_span")
+
+
+def profile_graph_report(clear: bool = False) -> dict:
+    """{kernel name: (total ms, launches)} of the LAST replay of the graphs captured while profile_kernels(2) was on."""
+    import ctypes
+
+    buf = ctypes.create_string_buffer(1 << 16)
+    _native.check(_native.lib().tt_profile_report_graph(buf, len(buf), 1 if clear else 0), "profile_graph_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(n))
+    return out
 
 
 def profile_report() -> dict:
