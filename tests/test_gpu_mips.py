@@ -39,6 +39,8 @@ GRID_CASES = [
     (600, 40000, 128, 100),  # several corpus parts per query block, merged in the finalize kernel
     (40, 3, 16, 3),          # k == corpus size
     (700, 257, 128, 64),
+    (300, 3000, 256, 50),    # BASELINE config-5 embedding width: one query tile per CTA, four K boxes
+    (130, 1500, 200, 10),    # 128 < d < 256, d not a multiple of 64
 ]
 
 

@@ -55,8 +55,8 @@ static_assert(CW == 16 || CW == 32, "chunk width");
 #ifndef TT_MIPS_SLEEP
 #define TT_MIPS_SLEEP 0
 #endif
-constexpr int EPI_WARPS = 4 * 2 * NBUF;          // one warp per (query tile, accumulator buffer, TMEM lane quarter)
-constexpr int SCREEN_THREADS = 128 + 32 * EPI_WARPS;
+// query tiles per CTA: two for d <= 128; one for 128 < d <= 256 (the operand tiles are twice as large)
+constexpr int ne_of(int DP) { return DP <= 128 ? 2 : 1; }
 
 // ---- packed keys: (order-preserving score bits << 32) | ~index ; larger key = better candidate ----------
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -150,12 +150,13 @@ __device__ void warp_bitonic_merge_desc(unsigned long long* s, int n, int lane) 
 
 struct ScreenArgs {
   int nq, nc, kp;
+  int NE;        // query tiles per CTA (= ne_of(DP))
   int G;         // grid size
   int R;         // full rounds: q-blocks [0, R*G) are scanned over the whole corpus
   int r, S;      // tail: r q-blocks, each split into S corpus parts
   int CT;        // corpus tiles
-  unsigned long long* lists;  // [G][2][128][LCAP] scratch
-  unsigned long long* part;   // [slots][2][128][kp] per-unit results (best kp, unsorted beyond "top kp")
+  unsigned long long* lists;  // [G][NE][NBUF][128][LCAP] scratch
+  unsigned long long* part;   // [slots][NE][NBUF][128][kp] per-unit results (sorted, zero padded)
 #ifdef TT_MIPS_BRINGUP
   int dbg;
   long long* trace;  // [tile][16] clock stamps of one epilogue warp of CTA 0
@@ -164,13 +165,17 @@ struct ScreenArgs {
 
 template <int DP>
 struct ScreenCfg {
+  static constexpr int NE = ne_of(DP);
+  static constexpr int EPI_WARPS = 4 * NE * NBUF;  // one warp per (query tile, accumulator buffer, TMEM lane quarter)
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int TMEM_COLS = NE * NBUF * CN;
   static constexpr int KBOX = DP / 64;
   static constexpr int Q_BYTES = QT * DP * 2;   // one query tile
   static constexpr int C_BYTES = CN * DP * 2;   // one corpus stage
-  static constexpr int STAGES = DP == 64 ? 4 : 3;
+  static constexpr int STAGES = DP == 64 ? 4 : (DP == 128 ? 3 : 2);
   static constexpr int SORT_BYTES = EPI_WARPS * LCAP * 8;  // one 4 KB scratch per epilogue warp
   static constexpr int TAG_BYTES = 0;
-  static constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * C_BYTES + SORT_BYTES + TAG_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = NE * Q_BYTES + STAGES * C_BYTES + SORT_BYTES + TAG_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -231,13 +236,14 @@ __device__ __noinline__ void warp_compact(unsigned long long* list, int n, int k
 }
 
 template <int DP>
-__global__ void __launch_bounds__(SCREEN_THREADS, 1)
+__global__ void __launch_bounds__(ScreenCfg<DP>::THREADS, 1)
 mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmc, const ScreenArgs a) {
   using Cfg = ScreenCfg<DP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sq = smem;                                   // 2 query tiles
-  uint8_t* sc = smem + 2 * Cfg::Q_BYTES;                // corpus ring
+  constexpr int NE = Cfg::NE;
+  uint8_t* sc = smem + NE * Cfg::Q_BYTES;               // corpus ring
   unsigned long long* ssort = reinterpret_cast<unsigned long long*>(sc + Cfg::STAGES * Cfg::C_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ssort) + Cfg::SORT_BYTES + Cfg::TAG_BYTES);
   uint64_t* q_full = bars;          // [1]
@@ -256,7 +262,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2 * NBUF; ++i) {
+    for (int i = 0; i < NE * NBUF; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 4);
     }
@@ -266,7 +272,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_holder, 512);
+  if (warp == 2) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -299,12 +305,12 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         int qb, j0, j1, slot;
         unit(u, qb, j0, j1, slot);
         mbar_wait(q_empty, (u & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_BYTES);
+        mbar_arrive_expect_tx(q_full, NE * Cfg::Q_BYTES);
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+        for (int e = 0; e < NE; ++e)
 #pragma unroll
           for (int b = 0; b < Cfg::KBOX; ++b)
-            tma_load_2d(sq + e * Cfg::Q_BYTES + b * (QT * 128), &tmq, q_full, b * 64, (qb * 2 + e) * QT);
+            tma_load_2d(sq + e * Cfg::Q_BYTES + b * (QT * 128), &tmq, q_full, b * 64, (qb * NE + e) * QT);
         for (int j = j0; j < j1; ++j) {
           mbar_wait_relaxed(&c_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&c_full[stage], Cfg::C_BYTES);
@@ -333,7 +339,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 #pragma unroll
           const uint32_t buf = t % NBUF, use = t / NBUF;  // accumulator buffer of this tile and its use count
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+          for (int e = 0; e < NE; ++e) {
             mbar_wait_relaxed(&d_empty[e * NBUF + buf], (use & 1) ^ 1);
             tc_fence_after();
 #pragma unroll
@@ -350,13 +356,13 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    const int e = (warp - 4) >> 3;        // query tile of the CTA
+    const int e = (warp - 4) / (4 * NBUF);  // query tile of the CTA
     const int par = ((warp - 4) >> 2) & 1;  // accumulator buffer = parity of the corpus tiles this warp scans
     const int q = warp & 3;         // TMEM lane quarter
     const int row = q * 32 + lane;  // row of the query tile owned by this thread
     unsigned long long* sscr = ssort + (warp - 4) * LCAP;  // unit-end sort scratch of this warp
     // this warp's 32 lists: [cta][e][row][LCAP]; a thread appends to the list of its own query row
-    unsigned long long* wlists = a.lists + ((((size_t)blockIdx.x * 2 + e) * NBUF + par) * QT + q * 32) * LCAP;
+    unsigned long long* wlists = a.lists + ((((size_t)blockIdx.x * NE + e) * NBUF + par) * QT + q * 32) * LCAP;
     unsigned long long* mylist = wlists + (size_t)lane * LCAP;
     const uint32_t park = smem_u32(sscr) + lane * (CW * 4);  // this row's parking slot in the warp's scratch
     const int sw = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);  // 16-byte pieces of a slot are XOR-swizzled against bank conflicts
@@ -495,7 +501,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
         for (int i = lane; i < ns; i += 32) sscr[i] = i < n ? list[i] : 0ull;
         __syncwarp();
         warp_sort_desc(sscr, ns, lane);
-        unsigned long long* dst = a.part + ((((size_t)slot * 2 + e) * NBUF + par) * QT + q * 32 + r) * a.kp;
+        unsigned long long* dst = a.part + ((((size_t)slot * NE + e) * NBUF + par) * QT + q * 32 + r) * a.kp;
         for (int i = lane; i < a.kp; i += 32) dst[i] = sscr[i];
         __syncwarp();
       }
@@ -506,7 +512,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -515,7 +521,7 @@ mips_screen_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 struct FinalArgs {
   int nq, nc, d, k, kp;
-  int G, R, r, S;
+  int NE, G, R, r, S;
   const unsigned long long* part;
   const float* q32;
   long long ldq;
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(128) mips_finalize_kernel(const FinalArgs a) {
   const long long row = (long long)blockIdx.x * 4 + warp;
   if (row >= a.nq) return;
   unsigned long long* s = ssort_all[warp];
-  const int qtile = (int)(row / QT), qb = qtile >> 1, e = qtile & 1, rr = (int)(row % QT);
+  const int qtile = (int)(row / QT), qb = qtile / a.NE, e = qtile % a.NE, rr = (int)(row % QT);
   int slot0, nparts;
   if (qb < a.R * a.G) { slot0 = qb; nparts = 1; }
   else { slot0 = a.R * a.G + (qb - a.R * a.G) * a.S; nparts = a.S; }
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(128) mips_finalize_kernel(const FinalArgs a) {
   // s[0, KP_MAX); the next part is laid behind it in REVERSE order, which makes the 2 KP_MAX keys a bitonic sequence,
   // and one merge pass set sorts them.
   for (int p = 0; p < nparts * NBUF; ++p) {
-    const unsigned long long* src = a.part + ((((size_t)(slot0 + p / NBUF) * 2 + e) * NBUF + p % NBUF) * QT + rr) * a.kp;
+    const unsigned long long* src = a.part + ((((size_t)(slot0 + p / NBUF) * a.NE + e) * NBUF + p % NBUF) * QT + rr) * a.kp;
     if (p == 0) {
       for (int i = lane; i < KP_MAX; i += 32) s[i] = i < a.kp ? src[i] : 0ull;
     } else {
@@ -573,16 +579,17 @@ __global__ void __launch_bounds__(128) mips_finalize_kernel(const FinalArgs a) {
 }
 
 struct Plan {
-  int DP, kp, NQB, CT, G, R, r, S, slots;
+  int DP, NE, kp, NQB, CT, G, R, r, S, slots;
 };
 
 static int make_plan(long long nq, long long nc, long long d, long long k, Plan& p) {
-  p.DP = d <= 64 ? 64 : 128;
+  p.DP = d <= 64 ? 64 : (d <= 128 ? 128 : 256);
+  p.NE = ne_of(p.DP);
   long long kp = k + (k / 4 > 32 ? k / 4 : 32);
   if (kp > nc) kp = nc;
   if (kp > KP_MAX) kp = KP_MAX;
   p.kp = (int)kp;
-  p.NQB = (int)((nq + 2 * QT - 1) / (2 * QT));
+  p.NQB = (int)((nq + p.NE * QT - 1) / (p.NE * QT));
   p.CT = (int)((nc + CN - 1) / CN);
   const int sms = num_sms();
   p.G = sms;
@@ -613,7 +620,7 @@ static int make_plan(long long nq, long long nc, long long d, long long k, Plan&
 size_t mips_workspace_bytes(long long Q, long long C, long long d, long long k) {
   Plan p;
   make_plan(Q, C, d, k, p);
-  return (size_t)p.G * 2 * NBUF * QT * LCAP * 8 + (size_t)p.slots * 2 * NBUF * QT * p.kp * 8 + 1024;
+  return (size_t)p.G * p.NE * NBUF * QT * LCAP * 8 + (size_t)p.slots * p.NE * NBUF * QT * p.kp * 8 + 1024;
 }
 
 template <int DP>
@@ -625,7 +632,7 @@ static int launch_screen(const CUtensorMap& tq, const CUtensorMap& tc, const Scr
     configured = true;
   }
   KernelSpan span("mips_screen_kernel", st);
-  mips_screen_kernel<DP><<<a.G, SCREEN_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tc, a);
+  mips_screen_kernel<DP><<<a.G, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tq, tc, a);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -636,7 +643,7 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
               float* scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
   TT_CHECK(nq > 0 && nc > 0 && d > 0, "mips_topk: empty problem");
   TT_CHECK(k > 0 && k <= nc, "mips_topk: selected index k out of range (k=%lld, corpus %lld)", k, nc);
-  TT_CHECK(d <= 128, "mips_topk: embedding dim %lld > 128 is not supported by the fused kernel", d);
+  TT_CHECK(d <= 256, "mips_topk: embedding dim %lld > 256 is not supported by the fused kernel", d);
   TT_CHECK(k <= KP_MAX - 32, "mips_topk: k=%lld > %d is not supported by the fused kernel", k, KP_MAX - 32);
   TT_CHECK(nc < (1ll << 32) - 1, "mips_topk: corpus too large for 32-bit row indices");
   TT_CHECK((ldq % 8) == 0 && (ldc % 8) == 0 && ((uintptr_t)Q16 % 16) == 0 && ((uintptr_t)C16 % 16) == 0,
@@ -645,7 +652,7 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
   make_plan(nq, nc, d, k, p);
   TT_CHECK(ws_bytes >= mips_workspace_bytes(nq, nc, d, k), "mips_topk: workspace too small");
   ScreenArgs a;
-  a.nq = (int)nq; a.nc = (int)nc; a.kp = p.kp;
+  a.nq = (int)nq; a.nc = (int)nc; a.kp = p.kp; a.NE = p.NE;
   a.G = p.G; a.R = p.R; a.r = p.r; a.S = p.S; a.CT = p.CT;
   a.lists = (unsigned long long*)ws;
 #ifdef TT_MIPS_BRINGUP
@@ -658,17 +665,18 @@ int mips_topk(const void* Q16, long long ldq, const void* C16, long long ldc, co
     a.trace = trace_dev;
   }
 #endif
-  a.part = a.lists + (size_t)p.G * 2 * NBUF * QT * LCAP;
+  a.part = a.lists + (size_t)p.G * p.NE * NBUF * QT * LCAP;
   CUtensorMap tq, tc;
   int rc = make_tmap_bf16(&tq, Q16, d, nq, ldq, 64, QT);
   if (rc) return rc;
   rc = make_tmap_bf16(&tc, C16, d, nc, ldc, 64, CN);
   if (rc) return rc;
-  rc = p.DP == 64 ? launch_screen<64>(tq, tc, a, stream) : launch_screen<128>(tq, tc, a, stream);
+  rc = p.DP == 64 ? launch_screen<64>(tq, tc, a, stream)
+                  : (p.DP == 128 ? launch_screen<128>(tq, tc, a, stream) : launch_screen<256>(tq, tc, a, stream));
   if (rc) return rc;
   FinalArgs f;
   f.nq = (int)nq; f.nc = (int)nc; f.d = (int)d; f.k = (int)k; f.kp = p.kp;
-  f.G = p.G; f.R = p.R; f.r = p.r; f.S = p.S;
+  f.NE = p.NE; f.G = p.G; f.R = p.R; f.r = p.r; f.S = p.S;
   f.part = a.part;
   f.q32 = Q32; f.ldq = ldq32; f.c32 = C32; f.ldc = ldc32;
   f.idx_out = idx; f.score_out = scores;
