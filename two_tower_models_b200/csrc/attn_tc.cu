@@ -207,11 +207,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const AttnTcArgs a) 
       tc_fence_after();
       const bool wr = seq < a.nseq && i < a.q_rows;
       bf16* dst = a.out + (seq * a.q_rows + i) * a.ldo;
+      const bool st32 = ((reinterpret_cast<uintptr_t>(a.out) | (uintptr_t)(a.ldo * 2)) & 31) == 0;
       for (int c = 0; c < a.D / 32; ++c) {
         float o[32];
         tmem_ld32(lane_base + O_COL + c * 32, o);
         tmem_wait_ld();
-        if (wr) {
+        if (wr && st32) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            st_global_32B(dst + c * 32 + k * 16, pack_bf16x2(o[16 * k + 0], o[16 * k + 1]), pack_bf16x2(o[16 * k + 2], o[16 * k + 3]),
+                          pack_bf16x2(o[16 * k + 4], o[16 * k + 5]), pack_bf16x2(o[16 * k + 6], o[16 * k + 7]),
+                          pack_bf16x2(o[16 * k + 8], o[16 * k + 9]), pack_bf16x2(o[16 * k + 10], o[16 * k + 11]),
+                          pack_bf16x2(o[16 * k + 12], o[16 * k + 13]), pack_bf16x2(o[16 * k + 14], o[16 * k + 15]));
+        } else if (wr) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint4 u;
@@ -417,8 +425,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constan
             u0.x = pack_bf16x2(o[0], o[1]); u0.y = pack_bf16x2(o[2], o[3]); u0.z = pack_bf16x2(o[4], o[5]); u0.w = pack_bf16x2(o[6], o[7]);
             u1.x = pack_bf16x2(o[8], o[9]); u1.y = pack_bf16x2(o[10], o[11]); u1.z = pack_bf16x2(o[12], o[13]); u1.w = pack_bf16x2(o[14], o[15]);
             bf16* d2 = dst + part * a.D + c * 16;
-            *reinterpret_cast<uint4*>(d2) = u0;
-            *reinterpret_cast<uint4*>(d2 + 8) = u1;
+            if ((reinterpret_cast<uintptr_t>(d2) & 31) == 0) {
+              st_global_32B(d2, u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w);
+            } else {
+              *reinterpret_cast<uint4*>(d2) = u0;
+              *reinterpret_cast<uint4*>(d2 + 8) = u1;
+            }
           }
         }
       tc_fence_before();

@@ -412,7 +412,8 @@ ce_bwd3_kernel(const __grid_constant__ TmapSet tmx, const __grid_constant__ Tmap
         // would touch 32 different 128-byte lines (the first drafts did: 4000 cycles per drain, and the flood of partial
         // sectors delayed the TMA loads of the next segment).  Each warp transposes through a private slice of the X
         // staging buffer (idle after stage_x): CHF floats of its 32 rows per round, written with an XOR swizzle,
-        // read back so that 4 (2) consecutive lanes cover 64 (32) contiguous bytes of a row.
+        // read back so that 4 (2) consecutive lanes cover 64 (32) contiguous bytes of a row.  (Four 32-byte stores per
+        // thread straight from registers - full sectors, no transpose - measured 82.9 vs 80.5 us for both passes.)
         constexpr int CHF = DP == 64 ? 8 : 16;          // floats of a row per round
         constexpr int CPR = CHF / 4;                    // 16-byte chunks per row and round
         constexpr int RPI = 32 / CPR;                   // rows per read-back instruction

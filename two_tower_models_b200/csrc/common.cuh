@@ -55,6 +55,14 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One 32-byte store = one full L2 sector per instruction (two 16-byte stores are two half-sector transactions; the
+// row-per-lane epilogues of the tensor-core kernels are bound by that count).  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_32B(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

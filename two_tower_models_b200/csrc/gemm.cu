@@ -258,6 +258,13 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (n0 + j < g.N) atomicAdd(cp + j, v[j]);
+            } else if (full && g.vec32 == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(cp + j * 8), "f"(v[8 * j]),
+                             "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]),
+                             "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
+                             : "memory");
             } else if (full && g.vec32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -270,7 +277,17 @@ gemm_kernel(const __grid_constant__ GemmBatch bt) {
           }
           if (g.c16 != nullptr) {
             bf16* cp = g.c16 + row * g.ldc16 + n0;
-            if (full && g.vec16) {
+            if (full && g.vec16 == 2) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(cp + j * 16), "r"(o[0]),
+                             "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                             : "memory");
+              }
+            } else if (full && g.vec16) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 o;
@@ -394,6 +411,9 @@ static int prepare(const GemmDesc& d, int BN, int share, GemmArgs& g, CUtensorMa
   g.colsum = d.colsum;
   g.vec32 = d.c32 && (d.ldc32 % 4 == 0) && ((uintptr_t)d.c32 % 16 == 0);
   g.vec16 = d.c16 && (d.ldc16 % 8 == 0) && ((uintptr_t)d.c16 % 16 == 0);
+  // 32-byte stores (one full L2 sector per instruction instead of two half-sector writes)
+  if (g.vec16 && (d.ldc16 % 16 == 0) && ((uintptr_t)d.c16 % 32 == 0)) g.vec16 = 2;
+  if (g.vec32 && (d.ldc32 % 8 == 0) && ((uintptr_t)d.c32 % 32 == 0)) g.vec32 = 2;
   g.vecmask = d.relu_mask && (d.ld_mask % 8 == 0) && ((uintptr_t)d.relu_mask % 16 == 0);
   g.mn_lbo = BK * 128; g.mn_sbo = 1024; g.mn_kadv = 2048;
   g.dbg = getenv("TT_GEMM_DBG") ? atoi(getenv("TT_GEMM_DBG")) : 0;

@@ -94,6 +94,11 @@ __device__ __forceinline__ void pack32(const float* v, uint32_t* p) {
   for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const uint32_t* p) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {  // full-sector stores
+    st_global_32B(dst, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]);
+    st_global_32B(dst + 16, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15]);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(dst + j * 8) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
@@ -372,9 +377,17 @@ tower_fwd_kernel(const __grid_constant__ TowerBatch tb) {
         bias_act(v[c], sBias + HID + D + col + c * 32, false);
         if (row_ok) {
           float* dst = ta.emb32 + (long long)grow * ta.ld_emb32 + col + c * 32;
+          if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              st_global_32B(dst + 8 * j, __float_as_uint(v[c][8 * j]), __float_as_uint(v[c][8 * j + 1]), __float_as_uint(v[c][8 * j + 2]),
+                            __float_as_uint(v[c][8 * j + 3]), __float_as_uint(v[c][8 * j + 4]), __float_as_uint(v[c][8 * j + 5]),
+                            __float_as_uint(v[c][8 * j + 6]), __float_as_uint(v[c][8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+          }
           pack32(v[c], pk);
           store_bf16x32(ta.emb16 + (long long)grow * ta.ld_emb16 + col + c * 32, pk);
         }
