@@ -89,6 +89,21 @@ int gather_rows_f32(const float* table, long long table_rows, long long dim, con
 // dense embedding gradient: table_grad[ids[i], :] += src[i, :]   (duplicates accumulate, like
 // embedding_dense_backward in the reference's autograd)
 // ---------------------------------------------------------------------------------------------
+// 16-byte vector reduction: one L2 atomic transaction for four columns
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 load4_as_f32(const bf16* s16, const float* s32, long long off) {
+  if (s16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(s16 + off);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(s32 + off);
+}
+// one warp per source row; VEC: a lane owns 4 consecutive columns (dim % 4 == 0, 16-byte aligned rows on both sides)
+template <bool VEC>
 __global__ void scatter_add_rows_kernel(const bf16* __restrict__ s16, const float* __restrict__ s32, long long ld_src,
                                         const long long* __restrict__ ids, long long n, int dim,
                                         float* __restrict__ grad, long long table_rows) {
@@ -98,17 +113,31 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ s16, const floa
   const long long id = ids[row];
   if (id < 0 || id >= table_rows) return;
   float* g = grad + id * dim;
-  for (int c = lane; c < dim; c += 32) {
-    const float v = s16 ? __bfloat162float(s16[row * ld_src + c]) : s32[row * ld_src + c];
-    atomicAdd(g + c, v);
+  if (VEC) {
+    for (int c = lane * 4; c < dim; c += 128) {
+      const float4 v = load4_as_f32(s16, s32, row * ld_src + c);
+      red_add_v4(g + c, v.x, v.y, v.z, v.w);
+    }
+  } else {
+    for (int c = lane; c < dim; c += 32) {
+      const float v = s16 ? __bfloat162float(s16[row * ld_src + c]) : s32[row * ld_src + c];
+      atomicAdd(g + c, v);
+    }
   }
+}
+static bool rows_vec4(const void* src16, const float* src32, long long ld_src, long long dim, const float* table_grad) {
+  const bool src_ok = src16 ? (ld_src % 4 == 0 && (uintptr_t)src16 % 8 == 0) : (ld_src % 4 == 0 && (uintptr_t)src32 % 16 == 0);
+  return dim % 4 == 0 && src_ok && (uintptr_t)table_grad % 16 == 0;
 }
 int scatter_add_rows(const void* src16, const float* src32, long long ld_src, const long long* ids, long long n,
                      long long dim, float* table_grad, long long table_rows, cudaStream_t stream) {
   if (n == 0) return 0;
   TT_CHECK((src16 != nullptr) != (src32 != nullptr), "scatter_add_rows: exactly one source");
   KernelSpan span("scatter_add_rows_kernel", stream);
-  scatter_add_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
+  if (rows_vec4(src16, src32, ld_src, dim, table_grad))
+    scatter_add_rows_kernel<true><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
+  else
+    scatter_add_rows_kernel<false><<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>((const bf16*)src16, src32, ld_src, ids, n, (int)dim, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -249,18 +278,49 @@ int history_gather_pool(const float* table, long long table_rows, long long D, c
 }
 
 // table_grad[ids[b,h], :] += dx[b*H+h, :] + dmean[b, :] / H
-__global__ void history_scatter_grad_kernel(const bf16* __restrict__ dx16, long long lddx, const float* __restrict__ dmean,
-                                            long long lddmean, const long long* __restrict__ ids, int H, int D,
-                                            float* __restrict__ grad, long long table_rows) {
-  const long long b = blockIdx.x;
+// One warp per batch row; VEC: a lane owns 4 consecutive columns, the H ids of the row are read once per warp.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+history_scatter_grad_kernel(const bf16* __restrict__ dx16, long long lddx, const float* __restrict__ dmean,
+                            long long lddmean, const long long* __restrict__ ids, long long B, int H, int D,
+                            float* __restrict__ grad, long long table_rows) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
   const float inv = 1.f / (float)H;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    const float dm = dmean ? dmean[b * lddmean + c] * inv : 0.f;
-    for (int h = 0; h < H; ++h) {
-      const long long id = ids[b * H + h];
-      if (id < 0 || id >= table_rows) continue;
-      const float v = (dx16 ? __bfloat162float(dx16[(b * H + h) * lddx + c]) : 0.f) + dm;
-      atomicAdd(grad + id * D + c, v);
+  if (VEC) {
+    for (int c0 = 0; c0 < D; c0 += 128) {  // every lane walks the loop (the ids travel by shuffle); idle lanes skip the work
+      const int c = c0 + lane * 4;
+      const bool act = c < D;
+      float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dmean && act) {
+        dm = *reinterpret_cast<const float4*>(dmean + b * lddmean + c);
+        dm.x *= inv; dm.y *= inv; dm.z *= inv; dm.w *= inv;
+      }
+      for (int h0 = 0; h0 < H; h0 += 32) {
+        const long long my_id = h0 + lane < H ? ids[b * H + h0 + lane] : -1;
+        const int hn = H - h0 < 32 ? H - h0 : 32;
+        for (int hh = 0; hh < hn; ++hh) {
+          const long long id = __shfl_sync(0xffffffffu, my_id, hh);
+          if (id < 0 || id >= table_rows || !act) continue;
+          float4 v = dm;
+          if (dx16) {
+            const float4 x = load4_as_f32(dx16, nullptr, (b * H + h0 + hh) * lddx + c);
+            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+          }
+          red_add_v4(grad + id * D + c, v.x, v.y, v.z, v.w);
+        }
+      }
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) {
+      const float dm = dmean ? dmean[b * lddmean + c] * inv : 0.f;
+      for (int h = 0; h < H; ++h) {
+        const long long id = ids[b * H + h];
+        if (id < 0 || id >= table_rows) continue;
+        const float v = (dx16 ? __bfloat162float(dx16[(b * H + h) * lddx + c]) : 0.f) + dm;
+        atomicAdd(grad + id * D + c, v);
+      }
     }
   }
 }
@@ -268,9 +328,14 @@ int history_scatter_grad(const void* dx16, long long lddx, const float* dmean, l
                          const long long* ids, long long B, long long H, long long D, float* table_grad,
                          long long table_rows, cudaStream_t stream) {
   if (B == 0) return 0;
-  const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
   KernelSpan span("history_scatter_grad_kernel", stream);
-  history_scatter_grad_kernel<<<(unsigned)B, threads, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, (int)H, (int)D, table_grad, table_rows);
+  const bool vec = D % 4 == 0 && (uintptr_t)table_grad % 16 == 0 && (!dx16 || (lddx % 4 == 0 && (uintptr_t)dx16 % 8 == 0)) &&
+                   (!dmean || (lddmean % 4 == 0 && (uintptr_t)dmean % 16 == 0));
+  const unsigned blocks = (unsigned)((B * 32 + 255) / 256);
+  if (vec)
+    history_scatter_grad_kernel<true><<<blocks, 256, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, B, (int)H, (int)D, table_grad, table_rows);
+  else
+    history_scatter_grad_kernel<false><<<blocks, 256, 0, stream>>>((const bf16*)dx16, lddx, dmean, lddmean, ids, B, (int)H, (int)D, table_grad, table_rows);
   TT_CUDA(cudaGetLastError());
   count_launch();
   return 0;
