@@ -1,5 +1,8 @@
 """Kernel timeline (torch.profiler / CUPTI) of one CUDA-graph replay of the batch-sharded training step on rank 0.
-usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dp_timeline.py [d]"""
+Run it under a SHORT timeout (`timeout 120 ...`): with 8 ranks under the profiler the process-group shutdown has hung
+once and, at 8x GPU-minutes per second, spent the rest of a round's GPU budget.  The script therefore leaves with
+os._exit after printing instead of tearing the group down.
+usage: timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dp_timeline.py [d]"""
 import os, sys, torch
 import torch.distributed as dist
 sys.path.insert(0, ".")
@@ -36,5 +39,6 @@ if rank == 0:
         gap = s - busy_end if s > busy_end else 0.0
         busy_end = max(busy_end, t)
         print(f"{s:8.1f} us  +{t - s:7.1f} us  gap {gap:6.1f}  {e.name[:95]}")
-    print(f"total span {ev[-1].time_range.end - t0:.1f} us")
-dist.destroy_process_group()
+    print(f"total span {ev[-1].time_range.end - t0:.1f} us", flush=True)
+sys.stdout.flush()
+os._exit(0)
