@@ -679,6 +679,16 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
                         float* lse, const float* labels, long long ldl, const float* uvw, long long TL, float* loss,
                         float* g, float* g_norm, void* ws, size_t ws_bytes, cudaStream_t stream, float* stats) {
   const void* V = Vp[0];
+  // the attached zero fills belong to THIS call: taken (and forgotten) before anything can fail, so that an error return
+  // never leaves pointers behind for a later launch
+  void* zero_ptr[2];
+  long long zero_bytes[2];
+  for (int z = 0; z < 2; ++z) {
+    zero_ptr[z] = g_zero_jobs.p[z];
+    zero_bytes[z] = g_zero_jobs.n[z];
+    g_zero_jobs.p[z] = nullptr;
+    g_zero_jobs.n[z] = 0;
+  }
   TT_CHECK(B > 0 && N > 0 && d > 0, "inbatch_ce_fwd: empty problem");
   TT_CHECK(d <= 256, "inbatch_ce_fwd: embedding dim %lld > 256 is not supported", d);
   TT_CHECK(target_offset >= 0 && target_offset + B <= N, "inbatch_ce_fwd: targets [%lld, %lld) outside the %lld item columns",
@@ -699,11 +709,9 @@ int inbatch_ce_loss_fwd(const void* U, long long ldu, const void* const* Vp, int
   dgo.U = (const bf16*)U; dgo.ldu = ldu; dgo.ldv = ldv; dgo.target_offset = target_offset; dgo.d = (int)d;
   dgo.rows_per_part = np == 1 ? N : rows_per_part;
   for (int p = 0; p < 8; ++p) dgo.Vp[p] = (const bf16*)Vp[p < np ? p : 0];
-  for (int z = 0; z < 2; ++z) {  // consume the attached zero fills
-    a.zero_ptr[z] = (uint8_t*)g_zero_jobs.p[z];
-    a.zero_bytes[z] = g_zero_jobs.n[z];
-    g_zero_jobs.p[z] = nullptr;
-    g_zero_jobs.n[z] = 0;
+  for (int z = 0; z < 2; ++z) {
+    a.zero_ptr[z] = (uint8_t*)zero_ptr[z];
+    a.zero_bytes[z] = zero_bytes[z];
   }
   a.trace = nullptr;
   if (const char* tr = getenv("TT_CE_TRACE")) a.trace = (long long*)strtoull(tr, nullptr, 0);
