@@ -23,5 +23,5 @@ print(f"# {lib}: SASS mnemonic counts per kernel (cuobjdump -sass); UTCHMMA = tc
 print("# UTMALDG = cp.async.bulk.tensor (TMA load), UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, HMMA = legacy mma.sync (none expected)")
 print(" ".join(f"{k:>8s}" for k in keys) + "   instr  kernel")
 for fn, c in counts.items():
-    name = re.sub(r"\(.*", "", demangle(fn)).replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*", "", demangle(fn).replace("(anonymous namespace)::", ""))
     print(" ".join(f"{c[k]:8d}" for k in keys) + f" {c['instructions']:7d}  {name}")
